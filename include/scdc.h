@@ -1,0 +1,159 @@
+/*
+ * scdc.h — C-ABI of the B200-native permutation-test engine behind scDiffCom's run_stat_analysis().
+ *
+ * This is the drop-in boundary. The reference has NO native interface today; the only
+ * "operator" on this path is the internal R function
+ *     run_stat_analysis(analysis_inputs, cci_dt_simple, iterations, return_distributions, score_type, verbose)
+ *     (reference R/utils_permutation.R:1-8, returns list(cci_raw, distributions) at :470-498).
+ * Its batch loop (R/utils_permutation.R:116-214, and :305-314 for return_distributions) together with
+ * run_stat_iteration (R/utils_permutation.R:501-603) and the compute_fast branch of run_simple_cci_analysis
+ * (R/utils_cci.R:171-261: aggregate_cells :441-462 + build_cci_or_drate("cci") :464-712) is what
+ * scdc_perm_counts() replaces. Everything before (:1-115: row subset, observed vectors, gene subset) and after
+ * (:215-499: p-values = counts / iterations, merge, NA / 1 fill) stays in R. The `.Call` wrapper an R maintainer
+ * adds (src/scdc_rcall.c) and the R glue are shown in INTEGRATION.md.
+ *
+ * Plain C: pointers and sizes only, no R types, no torch types, no C++ in the signatures. The library never
+ * throws, never calls exit/abort, never retains caller memory past return. There is NO CPU fallback: without a
+ * visible sm_100 device every compute entry point returns SCDC_ENOGPU.
+ */
+#ifndef SCDC_H
+#define SCDC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCDC_VERSION_STRING "0.1.0"
+
+/* error codes (0 = success) */
+enum {
+  SCDC_OK = 0,
+  SCDC_EINVAL = 1, /* bad argument / inconsistent problem (message in scdc_last_error) */
+  SCDC_ENOGPU = 2, /* no visible CUDA device of compute capability 10.x */
+  SCDC_ECUDA = 3,  /* CUDA runtime failure */
+  SCDC_ENCCL = 4,  /* NCCL failure (multi-GPU merge of the counters) */
+  SCDC_ENOMEM = 5  /* host or device allocation failure */
+};
+
+/* score_type (reference argument `score_type`, R/utils_cci.R:605,659) */
+enum { SCDC_SCORE_GEOMETRIC = 0, SCDC_SCORE_ARITHMETIC = 1 };
+
+/* precision modes. Only SCDC_FP64_EXACT is implemented: fp64 values, the reference's summation order. */
+enum { SCDC_FP64_EXACT = 0 };
+
+/* counts[] entry for a (row, column) whose observed value is NA (absent subunit): the reference yields NA there
+ * (R/utils_permutation.R:442-469); the .Call wrapper maps this to NA_real_. */
+#define SCDC_COUNT_NA UINT64_MAX
+
+/*
+ * The problem = analysis_inputs (R/utils_preprocessing.R:41-49, after the gene subset of
+ * R/utils_permutation.R:79-84) + sub_cci_template_iter (R/utils_permutation.R:85,114) + the observed vectors
+ * (R/utils_permutation.R:13,29-63), integer-encoded once by the caller:
+ *   ct_code   = match(metadata$cell_type, cell_types) - 1
+ *   cond_code = 0 for cond1, 1 for cond2 (NULL in detection mode)
+ *   sub_gene  = match(LIGAND_i / RECEPTOR_j, colnames(data_tr)) - 1, NA -> -1; one row per kept LRI,
+ *               row-major [n_lri][max_nL + max_nR] in the order L_1..L_nL, R_1..R_nR
+ *   row_*     = per tested row: index into the LRI table, emitter and receiver cell-type codes
+ *   observed  = column-major [n_rows x ncols]; ncols = 1 (detection: CCI_SCORE) or 3 + max_nL + max_nR
+ *               (differential: [DE = cond2 - cond1, cond1, cond2, L_1..L_nL diffs, R_1..R_nR diffs],
+ *               the column order of R/utils_permutation.R:580-598). NaN marks NA.
+ * The expression matrix is data_tr as it is: cells x genes dgCMatrix slots p, i, x (0-based CSC; within a gene
+ * column the cell indices ascend).
+ */
+typedef struct scdc_problem {
+  int32_t n_cells;      /* N */
+  int32_t n_genes;      /* G */
+  int32_t n_celltypes;  /* T  (<= 127 when n_conditions == 2, <= 255 otherwise) */
+  int32_t n_conditions; /* C: 1 = detection mode, 2 = differential mode */
+  int32_t n_lri;        /* L */
+  int32_t n_rows;       /* R_sub */
+  int32_t max_nL;       /* 1..2 (any >= 1 accepted) */
+  int32_t max_nR;       /* 1..3 (any >= 1 accepted) */
+  const int32_t* colptr;   /* [G + 1] */
+  const int32_t* rowidx;   /* [nnz] */
+  const double* values;    /* [nnz] */
+  const int32_t* ct_code;  /* [N] */
+  const int32_t* cond_code;/* [N] or NULL */
+  const int32_t* sub_gene; /* [L * (max_nL + max_nR)] */
+  const int32_t* row_lri;  /* [R_sub] */
+  const int32_t* row_emit; /* [R_sub] */
+  const int32_t* row_recv; /* [R_sub] */
+  const double* observed;  /* [R_sub * ncols], column-major */
+} scdc_problem;
+
+typedef struct scdc_options {
+  int64_t iterations;   /* replicates to run in THIS call (>= 1). p = counts / iterations is left to the caller */
+  uint64_t seed;        /* Philox key (reference: set.seed(seed), R/interaction_analysis.R:245) */
+  int64_t perm_offset;  /* global index of this call's first replicate: Philox counter = perm_offset + i, so any
+                           partition of [0, total) over calls / GPUs / processes reproduces the same labels */
+  int32_t score_type;   /* SCDC_SCORE_* */
+  int32_t n_gpus;       /* scdc_perm_counts only: 0 = all visible devices, k = first k devices */
+  int32_t precision;    /* SCDC_FP64_EXACT */
+  int32_t batch_size;   /* replicates per device launch; 0 = auto */
+  /* validation mode: the reference's own permuted labels, row-major [iterations][N] (replicate-major).
+     detection: perm_ct = sample(cell_type) codes (R/utils_permutation.R:509); perm_cond must be NULL.
+     differential: perm_cond = conditions after :536-541, perm_ct = cell types after :552-569. Both NULL -> the
+     labels are drawn on the device (Philox4x32-10, same strata, same distribution as base::sample). */
+  const uint8_t* perm_cond;
+  const uint8_t* perm_ct;
+  int32_t return_distributions; /* 1: also fill result.distributions (R/utils_permutation.R:304-426) */
+  int32_t reserved;
+} scdc_options;
+
+typedef struct scdc_stats {
+  double ms_total;      /* host wall time inside the call */
+  double ms_upload;     /* H2D of the problem (0 when a handle is reused) */
+  double ms_labels;     /* device time, label generation / upload + transpose (CUDA events) */
+  double ms_reduce;     /* device time, group-sum kernels (CUDA events) */
+  double ms_score;      /* device time, score / compare / count kernels (CUDA events) */
+  double ms_merge;      /* counter merge across GPUs + D2H */
+  double reduce_bytes;  /* algorithmic bytes of all group-sum launches ("algorithmic bytes") */
+  int64_t reduce_launches;
+  int64_t kernel_launches; /* all kernels launched by the call */
+  int64_t batch_size;   /* replicates per launch actually used */
+  int32_t n_gpus;       /* devices actually used */
+  int32_t reserved;
+} scdc_stats;
+
+typedef struct scdc_result {
+  uint64_t* counts;       /* [R_sub * ncols] column-major, caller-allocated; SCDC_COUNT_NA where observed is NaN */
+  double* distributions;  /* NULL, or caller-allocated [R_sub * ncols_d * iterations] (replicate-major blocks of a
+                             column-major R_sub x ncols_d matrix); ncols_d = 1 (detection) or 3 (DE, cond1, cond2) */
+  void* counts_device;    /* scdc_run only: NULL, or a DEVICE buffer of int64[R_sub * ncols] on the handle's device
+                             that receives the raw counts (NA entries = 0) for a caller-side collective */
+  scdc_stats stats;
+} scdc_result;
+
+/* One-shot entry point: what `.Call("C_scdc_perm_counts", ...)` binds. Uploads the problem, runs `iterations`
+ * replicates sharded over `n_gpus` devices (contiguous replicate ranges, replicated expression matrix), merges the
+ * integer counters with one ncclAllReduce(sum) and writes them to result->counts. */
+int scdc_perm_counts(const scdc_problem* problem, const scdc_options* options, scdc_result* result);
+
+/* Handle API: keep the problem resident on one device across calls (benchmarks, resumable / sharded runs:
+ * counts are additive over replicate ranges). */
+typedef struct scdc_handle scdc_handle;
+int scdc_create(const scdc_problem* problem, int32_t device, scdc_handle** out);
+int scdc_run(scdc_handle* handle, const scdc_options* options, scdc_result* result);
+void scdc_release(scdc_handle* handle);
+
+/* Observed-pass helper (reference aggregate_cells, R/utils_cci.R:441-462, on the ORIGINAL labels): group means of the
+ * expression and of 1*(x > 0) (detection rate, R/utils_cci.R:262-266), each [K x G] column-major with K = C * T and
+ * group index = cond_code * T + ct_code. Either output may be NULL. */
+int scdc_group_means(scdc_handle* handle, double* means, double* detection_rate);
+
+/* Debug / test hook: the labels scdc_run would draw on the device for replicates [perm_offset, perm_offset + n),
+ * row-major [n][N]. cond_out may be NULL in detection mode. */
+int scdc_draw_labels(scdc_handle* handle, uint64_t seed, int64_t perm_offset, int64_t n, uint8_t* cond_out,
+                     uint8_t* ct_out);
+
+const char* scdc_last_error(void); /* thread-local message of the last failing call on this thread */
+int scdc_device_count(void);       /* visible devices with compute capability 10.x (0 when there is none) */
+const char* scdc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDC_H */

@@ -1,0 +1,240 @@
+/*
+ * scdc_oracle.c — CPU ORACLE (test infrastructure, NOT the product path).
+ *
+ * Plain-C restatement of scDiffCom's permutation iteration on the integer-coded boundary of include/scdc.h, used
+ *   (1) by tests/ as the bit-exact checker of the CUDA path under uploaded labels,
+ *   (2) by bench.py's cpu_baseline / `--impl reference` legs as the timed CPU stand-in for the R path
+ *       (R is not installed in this image).
+ * Only tests/, __graft_entry__.smoke() and those bench legs may load it. Pinned against oracle_np.py (which is pinned
+ * against the reference's fixtures and known-answer tests) in tests/test_oracle_pins.py.
+ *
+ * Follows, per replicate (citations relative to /root/reference):
+ *   R/utils_cci.R:441-462   aggregate_cells: sums[group[cell]][gene] += x over each gene column in ascending cell
+ *                           order (the C loop behind DelayedArray::rowsum on a dgCMatrix; Bioconductor DelayedArray,
+ *                           unpinned, not vendored), then / table(group) recomputed from the permuted labels
+ *   R/utils_cci.R:464-712   build_cci_or_drate("cci"): gather subunit means per row, pmin(na.rm=TRUE), sqrt(L*R) or (L+R)/2
+ *   R/utils_cci.R:197-261   compute_fast outputs: cond1, cond2 scores, L_i / R_j cond2 - cond1 differences
+ *   R/utils_permutation.R:543-602  two passes (conditions permuted; then cell types permuted inside permuted conditions),
+ *                           columns [DE, cond1, cond2, L_1.., R_1..]
+ *   R/utils_permutation.R:139-211  counting: >=, abs() two-sided for DE and subunit columns
+ *
+ * oracle_philox_labels restates THIS repo's device label generator (scdiffcom_b200/csrc/scdc_kernels.cuh,
+ * k_draw_labels) — not a reference algorithm: the reference draws with base::sample on L'Ecuyer streams, which cannot
+ * be reproduced without R. It lets tests check the device generator bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+  int N, G, T, C, L, R, nL, nR;
+  const int32_t *colptr, *rowidx;
+  const double* values;
+  const int32_t *sub_gene, *row_lri, *row_emit, *row_recv;
+  const double* observed; /* column-major [R][ncols] */
+} oracle_problem;
+
+/* aggregate_cells: means[k*G + g] */
+static void aggregate_cells(const oracle_problem* p, const uint8_t* group, int K, double* means, double* ncell) {
+  memset(means, 0, sizeof(double) * (size_t)K * p->G);
+  memset(ncell, 0, sizeof(double) * (size_t)K);
+  for (int i = 0; i < p->N; ++i) ncell[group[i]] += 1.0; /* table(group) */
+  for (int g = 0; g < p->G; ++g)
+    for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) means[(size_t)group[p->rowidx[e]] * p->G + g] += p->values[e];
+  for (int k = 0; k < K; ++k)
+    for (int g = 0; g < p->G; ++g) means[(size_t)k * p->G + g] = means[(size_t)k * p->G + g] / ncell[k];
+}
+
+static double pmin_na_rm(const double* v, int n) {
+  double m = NAN;
+  for (int i = 0; i < n; ++i) {
+    if (isnan(v[i])) continue;
+    if (isnan(m) || v[i] < m) m = v[i];
+  }
+  return m;
+}
+
+/* build_cci_or_drate("cci") for one row and one condition: expr[s] = subunit means (NaN = NA), returns the score */
+static double row_score(const oracle_problem* p, const double* means, int cond, int row, int score_type, double* expr) {
+  const int nS = p->nL + p->nR, l = p->row_lri[row];
+  for (int s = 0; s < nS; ++s) {
+    int g = p->sub_gene[(size_t)l * nS + s];
+    int ct = (s < p->nL) ? p->row_emit[row] : p->row_recv[row];
+    expr[s] = (g < 0) ? NAN : means[(size_t)(cond * p->T + ct) * p->G + g];
+  }
+  double mL = pmin_na_rm(expr, p->nL), mR = pmin_na_rm(expr + p->nL, p->nR);
+  return score_type == 0 ? sqrt(mL * mR) : (mL + mR) / 2;
+}
+
+/*
+ * perm_cond / perm_ct: replicate-major [iterations][N] label codes (perm_cond NULL in detection mode).
+ * counts: column-major [R][ncols] uint64 (zeroed here). dist: NULL or [iterations][ncols_d][R].
+ * nthreads <= 0: all OpenMP threads.
+ */
+int oracle_perm_counts(int N, int G, int T, int C, int L, int R, int nL, int nR, const int32_t* colptr,
+                       const int32_t* rowidx, const double* values, const int32_t* ct_code, const int32_t* sub_gene,
+                       const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv, const double* observed,
+                       int64_t iterations, int score_type, const uint8_t* perm_cond, const uint8_t* perm_ct,
+                       uint64_t* counts, double* dist, int nthreads) {
+  oracle_problem P = {N, G, T, C, L, R, nL, nR, colptr, rowidx, values, sub_gene, row_lri, row_emit, row_recv, observed};
+  const int K = C * T, nS = nL + nR, ncols = (C == 2) ? 3 + nS : 1, ncols_d = (C == 2) ? 3 : 1;
+  memset(counts, 0, sizeof(uint64_t) * (size_t)R * ncols);
+  int bad = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    double* m1 = (double*)malloc(sizeof(double) * (size_t)K * G);
+    double* m2 = (double*)malloc(sizeof(double) * (size_t)K * G);
+    double* ncell = (double*)malloc(sizeof(double) * (size_t)K);
+    uint8_t* grp = (uint8_t*)malloc((size_t)N);
+    uint64_t* loc = (uint64_t*)calloc((size_t)R * ncols, sizeof(uint64_t));
+    if (!m1 || !m2 || !ncell || !grp || !loc) {
+#pragma omp atomic write
+      bad = 1;
+    } else {
+#pragma omp for schedule(dynamic, 1)
+      for (int64_t it = 0; it < iterations; ++it) {
+        const uint8_t* pct = perm_ct + (size_t)it * N;
+        double e1[16], e2[16];
+        if (C == 1) {
+          for (int i = 0; i < N; ++i) grp[i] = pct[i];
+          aggregate_cells(&P, grp, K, m2, ncell);
+          for (int r = 0; r < R; ++r) {
+            double sc = row_score(&P, m2, 0, r, score_type, e1);
+            if (sc >= observed[r]) ++loc[r];
+            if (dist) dist[(size_t)it * R + r] = sc;
+          }
+        } else {
+          const uint8_t* pcd = perm_cond + (size_t)it * N;
+          for (int i = 0; i < N; ++i) grp[i] = (uint8_t)(pcd[i] * T + ct_code[i]); /* pass 1: permuted condition, original type */
+          aggregate_cells(&P, grp, K, m1, ncell);
+          for (int i = 0; i < N; ++i) grp[i] = (uint8_t)(pcd[i] * T + pct[i]);     /* pass 2: permuted type inside permuted condition */
+          aggregate_cells(&P, grp, K, m2, ncell);
+          for (int r = 0; r < R; ++r) {
+            double s1c1 = row_score(&P, m1, 0, r, score_type, e1);
+            double s1c2 = row_score(&P, m1, 1, r, score_type, e2);
+            double de = s1c2 - s1c1;
+            double s2c1 = row_score(&P, m2, 0, r, score_type, e1 + 8); /* e1[8..] scratch */
+            double s2c2 = row_score(&P, m2, 1, r, score_type, e2 + 8);
+            if (fabs(de) >= fabs(observed[r])) ++loc[r];
+            if (s2c1 >= observed[(size_t)R + r]) ++loc[(size_t)R + r];
+            if (s2c2 >= observed[(size_t)2 * R + r]) ++loc[(size_t)2 * R + r];
+            for (int s = 0; s < nS; ++s) {
+              double d = e2[s] - e1[s]; /* cond2 - cond1, NaN when the subunit is NA */
+              if (fabs(d) >= fabs(observed[(size_t)(3 + s) * R + r])) ++loc[(size_t)(3 + s) * R + r];
+            }
+            if (dist) {
+              double* d = dist + ((size_t)it * ncols_d) * R + r;
+              d[0] = de; d[(size_t)R] = s2c1; d[(size_t)2 * R] = s2c2;
+            }
+          }
+        }
+      }
+#pragma omp critical
+      for (size_t i = 0; i < (size_t)R * ncols; ++i) counts[i] += loc[i];
+    }
+    free(m1); free(m2); free(ncell); free(grp); free(loc);
+  }
+  return bad;
+}
+
+/* aggregate_cells on given labels: out column-major [K][G] (out[g*K + k]); mode 1 = detection rate */
+int oracle_group_means(int N, int G, int K, const int32_t* colptr, const int32_t* rowidx, const double* values,
+                       const uint8_t* group, int mode, double* out) {
+  double* ncell = (double*)calloc((size_t)K, sizeof(double));
+  if (!ncell) return 1;
+  for (int i = 0; i < N; ++i) ncell[group[i]] += 1.0;
+  memset(out, 0, sizeof(double) * (size_t)K * G);
+  for (int g = 0; g < G; ++g)
+    for (int e = colptr[g]; e < colptr[g + 1]; ++e)
+      out[(size_t)g * K + group[rowidx[e]]] += mode ? (values[e] > 0 ? 1.0 : 0.0) : values[e];
+  for (int g = 0; g < G; ++g)
+    for (int k = 0; k < K; ++k) out[(size_t)g * K + k] = out[(size_t)g * K + k] / ncell[k];
+  free(ncell);
+  return 0;
+}
+
+/* ---- restatement of the device label generator (Philox4x32-10 + sequential urn draws) ------------------------------ */
+typedef struct {
+  uint32_t c0, c1, c2, c3, k0, k1, out[4];
+  int have;
+} philox_t;
+
+static void philox_refill(philox_t* s) {
+  uint32_t x0 = s->c0, x1 = s->c1, x2 = s->c2, x3 = s->c3, a = s->k0, b = s->k1;
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
+    uint32_t y0 = (uint32_t)(p1 >> 32) ^ x1 ^ a, y1 = (uint32_t)p1, y2 = (uint32_t)(p0 >> 32) ^ x3 ^ b, y3 = (uint32_t)p0;
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    a += 0x9E3779B9u; b += 0xBB67AE85u;
+  }
+  s->out[0] = x0; s->out[1] = x1; s->out[2] = x2; s->out[3] = x3;
+  s->have = 4;
+  if (++s->c0 == 0) ++s->c1;
+}
+static uint32_t philox_next(philox_t* s) {
+  if (s->have == 0) philox_refill(s);
+  uint32_t v = s->out[4 - s->have];
+  --s->have;
+  return v;
+}
+static uint32_t philox_bounded(philox_t* s, uint32_t range) {
+  uint64_t m = (uint64_t)philox_next(s) * range;
+  uint32_t l = (uint32_t)m;
+  if (l < range) {
+    uint32_t t = (0u - range) % range;
+    while (l < t) {
+      m = (uint64_t)philox_next(s) * range;
+      l = (uint32_t)m;
+    }
+  }
+  return (uint32_t)(m >> 32);
+}
+/* smallest k with n[0] + .. + n[k] > u */
+static int urn_pick(uint32_t* n, int T, uint32_t u) {
+  uint32_t acc = 0;
+  for (int k = 0; k < T; ++k) {
+    acc += n[k];
+    if (u < acc) { --n[k]; return k; }
+  }
+  return -1;
+}
+
+int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int32_t* cond_code, uint64_t seed,
+                         int64_t perm_offset, int64_t n, uint8_t* cond_out, uint8_t* ct_out) {
+  uint32_t* base = (uint32_t*)calloc((size_t)2 * T, sizeof(uint32_t));
+  uint32_t* remc = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)2 * T);
+  uint32_t* urn = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)2 * T);
+  if (!base || !remc || !urn) return 1;
+  for (int i = 0; i < N; ++i) ++base[(size_t)((C == 2) ? cond_code[i] : 0) * T + ct_code[i]];
+  for (int64_t q = 0; q < n; ++q) {
+    philox_t s = {0, 0, (uint32_t)(uint64_t)(perm_offset + q), (uint32_t)((uint64_t)(perm_offset + q) >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), {0, 0, 0, 0}, 0};
+    memcpy(remc, base, sizeof(uint32_t) * (size_t)2 * T);
+    memcpy(urn, base, sizeof(uint32_t) * (size_t)2 * T);
+    uint32_t tot[2] = {0, 0};
+    for (int t = 0; t < T; ++t) { tot[0] += base[t]; tot[1] += base[(size_t)T + t]; }
+    for (int i = 0; i < N; ++i) {
+      int c = 0;
+      if (C == 2) {
+        int t = ct_code[i];
+        uint32_t r0 = remc[t], r1 = remc[(size_t)T + t];
+        uint32_t u = philox_bounded(&s, r0 + r1);
+        c = (u < r0) ? 0 : 1;
+        --remc[(size_t)c * T + t];
+        cond_out[(size_t)q * N + i] = (uint8_t)c;
+      }
+      uint32_t u = philox_bounded(&s, tot[c]);
+      --tot[c];
+      ct_out[(size_t)q * N + i] = (uint8_t)urn_pick(urn + (size_t)c * T, T, u);
+    }
+  }
+  free(base); free(remc); free(urn);
+  return 0;
+}

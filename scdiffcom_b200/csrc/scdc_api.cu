@@ -1,0 +1,749 @@
+// scdc_api.cu — host side of the C-ABI declared in include/scdc.h: validation, upload, batch loop, counter merge.
+// The arithmetic lives in scdc_kernels.cuh. No CPU fallback: every compute entry point needs an sm_100 device.
+#include "../../include/scdc.h"
+#include "scdc_kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(e_ == cudaErrorMemoryAllocation ? SCDC_ENOMEM : SCDC_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                           \
+  } while (0)
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// device buffer with RAII
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t ensure(size_t count) { return (count <= n && p) ? cudaSuccess : alloc(count); }
+  cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+}  // namespace
+
+struct scdc_handle {
+  int device = 0;
+  int N = 0, G = 0, T = 0, C = 0, L = 0, R = 0, nL = 0, nR = 0, K = 0, ncols = 0, nS = 0;
+  size_t nnz = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+  // problem
+  DBuf<int> colptr, rowidx, segptr, rowidx_s, gene_order, sub_gene, row_lri, row_emit, row_recv;
+  DBuf<double> values, values_s, ngroup, obs;
+  DBuf<uint8_t> ct, cond;
+  DBuf<uint32_t> urn_init, expect;
+  std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
+  // per-run workspace (grown on demand)
+  DBuf<uint32_t> bits1, counts;
+  DBuf<uint8_t> lab2, up_cond, up_ct;
+  DBuf<double> M1, M2, dist;
+  DBuf<int> flag;
+  double ms_upload = 0;
+};
+
+namespace {
+
+int count_sm100_devices(std::vector<int>* ids) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int found = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) {
+      ++found;
+      if (ids) ids->push_back(d);
+    }
+  }
+  return found;
+}
+
+int validate_problem(const scdc_problem* p) {
+  if (!p) return fail(SCDC_EINVAL, "problem is NULL");
+  if (p->n_cells < 1 || p->n_genes < 1 || p->n_celltypes < 1 || p->n_lri < 1 || p->n_rows < 0)
+    return fail(SCDC_EINVAL, "non-positive dimension (N=%d G=%d T=%d L=%d R=%d)", p->n_cells, p->n_genes,
+                p->n_celltypes, p->n_lri, p->n_rows);
+  if (p->n_conditions != 1 && p->n_conditions != 2) return fail(SCDC_EINVAL, "n_conditions must be 1 or 2");
+  if (p->n_celltypes * p->n_conditions > 254)
+    return fail(SCDC_EINVAL, "n_celltypes * n_conditions = %d exceeds the 8-bit label range (254)",
+                p->n_celltypes * p->n_conditions);
+  if (p->max_nL < 1 || p->max_nR < 1 || p->max_nL + p->max_nR > 8)
+    return fail(SCDC_EINVAL, "max_nL/max_nR must be >= 1 with max_nL + max_nR <= 8");
+  if (!p->colptr || !p->rowidx || !p->values || !p->ct_code || !p->sub_gene || (p->n_rows > 0 && (!p->row_lri || !p->row_emit || !p->row_recv || !p->observed)))
+    return fail(SCDC_EINVAL, "NULL array in problem");
+  if (p->n_conditions == 2 && !p->cond_code) return fail(SCDC_EINVAL, "cond_code is NULL in differential mode");
+  const int N = p->n_cells, G = p->n_genes, T = p->n_celltypes, C = p->n_conditions;
+  if (p->colptr[0] != 0) return fail(SCDC_EINVAL, "colptr[0] != 0");
+  for (int g = 0; g < G; ++g) {
+    if (p->colptr[g + 1] < p->colptr[g]) return fail(SCDC_EINVAL, "colptr not non-decreasing at gene %d", g);
+    for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) {
+      int c = p->rowidx[e];
+      if (c < 0 || c >= N) return fail(SCDC_EINVAL, "rowidx out of range at entry %d", e);
+      if (e > p->colptr[g] && c <= p->rowidx[e - 1])
+        return fail(SCDC_EINVAL, "rowidx not strictly ascending inside gene column %d", g);
+    }
+  }
+  std::vector<int64_t> ng((size_t)C * T, 0);
+  for (int i = 0; i < N; ++i) {
+    int t = p->ct_code[i];
+    int c = (C == 2) ? p->cond_code[i] : 0;
+    if (t < 0 || t >= T) return fail(SCDC_EINVAL, "ct_code[%d] = %d out of range", i, t);
+    if (c < 0 || c >= C) return fail(SCDC_EINVAL, "cond_code[%d] = %d out of range", i, c);
+    ++ng[(size_t)c * T + t];
+  }
+  for (size_t k = 0; k < ng.size(); ++k)
+    if (ng[k] < 1)
+      return fail(SCDC_EINVAL, "group (condition %d, cell type %d) has no cells", (int)(k / T), (int)(k % T));
+  const int nS = p->max_nL + p->max_nR;
+  for (int l = 0; l < p->n_lri; ++l) {
+    for (int s = 0; s < nS; ++s) {
+      int g = p->sub_gene[(size_t)l * nS + s];
+      if (g < -1 || g >= G) return fail(SCDC_EINVAL, "sub_gene[%d][%d] = %d out of range", l, s, g);
+    }
+    if (p->sub_gene[(size_t)l * nS] < 0 || p->sub_gene[(size_t)l * nS + p->max_nL] < 0)
+      return fail(SCDC_EINVAL, "LRI %d lacks LIGAND_1 or RECEPTOR_1", l);
+  }
+  for (int r = 0; r < p->n_rows; ++r) {
+    if (p->row_lri[r] < 0 || p->row_lri[r] >= p->n_lri || p->row_emit[r] < 0 || p->row_emit[r] >= T ||
+        p->row_recv[r] < 0 || p->row_recv[r] >= T)
+      return fail(SCDC_EINVAL, "row %d has an out-of-range LRI / emitter / receiver code", r);
+  }
+  return SCDC_OK;
+}
+
+int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* o) {
+  if (!o) return fail(SCDC_EINVAL, "options is NULL");
+  if (o->iterations < 1) return fail(SCDC_EINVAL, "iterations must be >= 1");
+  if (o->perm_offset < 0) return fail(SCDC_EINVAL, "perm_offset must be >= 0");
+  if (o->score_type != SCDC_SCORE_GEOMETRIC && o->score_type != SCDC_SCORE_ARITHMETIC)
+    return fail(SCDC_EINVAL, "unknown score_type %d", o->score_type);
+  if (o->precision != SCDC_FP64_EXACT) return fail(SCDC_EINVAL, "only precision = SCDC_FP64_EXACT is implemented");
+  if (o->batch_size < 0) return fail(SCDC_EINVAL, "batch_size must be >= 0");
+  if (C == 1 && o->perm_cond) return fail(SCDC_EINVAL, "perm_cond given in detection mode");
+  if (C == 2 && ((o->perm_cond != nullptr) != (o->perm_ct != nullptr)))
+    return fail(SCDC_EINVAL, "differential validation mode needs both perm_cond and perm_ct");
+  return SCDC_OK;
+}
+
+// Fenwick tree (1-based) over counts n[0..T)
+void fenwick_build(const uint32_t* n, int T, uint32_t* tree /*[T], tree[i-1] = node i*/) {
+  for (int i = 1; i <= T; ++i) {
+    uint32_t s = 0;
+    for (int j = i - (i & -i) + 1; j <= i; ++j) s += n[j - 1];
+    tree[i - 1] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* scdc_last_error(void) { return g_err.c_str(); }
+const char* scdc_version(void) { return SCDC_VERSION_STRING; }
+int scdc_device_count(void) { return count_sm100_devices(nullptr); }
+
+void scdc_release(scdc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
+  if (!out) return fail(SCDC_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  std::vector<int> ids;
+  if (count_sm100_devices(&ids) == 0)
+    return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
+  if (device < 0) device = ids[0];
+  if (std::find(ids.begin(), ids.end(), (int)device) == ids.end())
+    return fail(SCDC_ENOGPU, "device %d is not a visible compute-capability-10.x device", device);
+  const double t0 = now_ms();
+  CU(cudaSetDevice(device));
+  std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
+  if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
+  h->device = device;
+  h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
+  h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
+  h->ncols = (h->C == 2) ? 3 + h->nS : 1;
+  h->nnz = (size_t)p->colptr[h->G];
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  int v = 0;
+  CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  h->num_sms = v;
+  CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  h->smem_optin = (size_t)v;
+  const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K;
+  cudaStream_t s = h->stream;
+  try {
+    std::vector<uint8_t> ct8(N), cond8(N, 0);
+    std::vector<uint32_t> ng((size_t)K, 0);
+    for (int i = 0; i < N; ++i) {
+      ct8[i] = (uint8_t)p->ct_code[i];
+      if (C == 2) cond8[i] = (uint8_t)p->cond_code[i];
+      ++ng[(size_t)cond8[i] * T + ct8[i]];
+    }
+    std::vector<double> ngd(K);
+    for (int k = 0; k < K; ++k) ngd[k] = (double)ng[k];
+    // gene order: heaviest columns first (tail balance)
+    std::vector<int> order(G);
+    for (int g = 0; g < G; ++g) order[g] = g;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return (p->colptr[a + 1] - p->colptr[a]) > (p->colptr[b + 1] - p->colptr[b]);
+    });
+    // urn initial state for K1
+    std::vector<uint32_t> init;
+    if (C == 2) {
+      init.resize((size_t)4 * T + 2);
+      for (int t = 0; t < T; ++t) { init[t] = ng[t]; init[T + t] = ng[(size_t)T + t]; }
+      fenwick_build(&ng[0], T, &init[(size_t)2 * T]);
+      fenwick_build(&ng[(size_t)T], T, &init[(size_t)3 * T]);
+      uint32_t n0 = 0, n1 = 0;
+      for (int t = 0; t < T; ++t) { n0 += ng[t]; n1 += ng[(size_t)T + t]; }
+      init[(size_t)4 * T] = n0; init[(size_t)4 * T + 1] = n1;
+    } else {
+      init.resize((size_t)T + 2);
+      fenwick_build(&ng[0], T, &init[0]);
+      init[T] = (uint32_t)N; init[(size_t)T + 1] = 0;
+    }
+    CU(h->colptr.upload(p->colptr, (size_t)G + 1, s));
+    CU(h->rowidx.upload(p->rowidx, h->nnz, s));
+    CU(h->values.upload(p->values, h->nnz, s));
+    CU(h->ct.upload(ct8.data(), N, s));
+    CU(h->cond.upload(cond8.data(), N, s));
+    CU(h->ngroup.upload(ngd.data(), K, s));
+    CU(h->expect.upload(ng.data(), K, s));
+    CU(h->gene_order.upload(order.data(), G, s));
+    CU(h->urn_init.upload(init.data(), init.size(), s));
+    CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
+    CU(h->row_lri.upload(p->row_lri, h->R, s));
+    CU(h->row_emit.upload(p->row_emit, h->R, s));
+    CU(h->row_recv.upload(p->row_recv, h->R, s));
+    CU(h->obs.upload(p->observed, (size_t)h->R * h->ncols, s));
+    h->obs_na.resize((size_t)h->R * h->ncols);
+    for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(p->observed[i]) ? 1 : 0;
+    std::vector<int> segptr, rows_s;
+    std::vector<double> vals_s;
+    if (C == 2) {
+      // pass-1 copy of the matrix: inside each gene column, entries stably sorted by cell type
+      segptr.resize((size_t)G * (T + 1));
+      rows_s.resize(h->nnz);
+      vals_s.resize(h->nnz);
+      std::vector<int> cnt(T + 1);
+      for (int g = 0; g < G; ++g) {
+        const int b = p->colptr[g], e = p->colptr[g + 1];
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int i = b; i < e; ++i) ++cnt[ct8[p->rowidx[i]] + 1];
+        int* sp = &segptr[(size_t)g * (T + 1)];
+        sp[0] = b;
+        for (int t = 0; t < T; ++t) sp[t + 1] = sp[t] + cnt[t + 1];
+        for (int t = 0; t < T; ++t) cnt[t] = sp[t];
+        for (int i = b; i < e; ++i) {
+          int dst = cnt[ct8[p->rowidx[i]]]++;
+          rows_s[dst] = p->rowidx[i];
+          vals_s[dst] = p->values[i];
+        }
+      }
+      CU(h->segptr.upload(segptr.data(), segptr.size(), s));
+      CU(h->rowidx_s.upload(rows_s.data(), h->nnz, s));
+      CU(h->values_s.upload(vals_s.data(), h->nnz, s));
+    }
+    CU(h->flag.alloc(1));
+    CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+  } catch (const std::bad_alloc&) {
+    return fail(SCDC_ENOMEM, "host allocation failed while staging the problem");
+  }
+  h->ms_upload = now_ms() - t0;
+  *out = h.release();
+  return SCDC_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct ScatterPlan {
+  int J, W, blocks_per_sm;
+  size_t smem;
+};
+
+ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
+  const int K = h->K;
+  int J = (K <= 16) ? 4 : (K <= 32 ? 2 : 1);
+  J = env_int("SCDC_J", J);
+  if (J != 1 && J != 2 && J != 4) J = 1;
+  while (J > 1 && (Bpad % (32 * J)) != 0) J >>= 1;
+  const size_t per_warp = (size_t)K * J * 256 + 512;
+  const int nCJ = Bpad / (32 * J);
+  const size_t cap = h->smem_optin ? h->smem_optin : 232448;
+  int bestW = 1, best_warps = 0, best_bps = 1;
+  for (int W = 1; W <= 8 && W <= nCJ; ++W) {
+    size_t need = per_warp * W;
+    if (need > cap) break;
+    int bps = (int)std::min<size_t>(32, (233472 - 0) / (need + 1024));
+    if (bps < 1) bps = 1;
+    int warps = std::min(64, bps * W);
+    if (warps > best_warps || (warps == best_warps && W > bestW)) { best_warps = warps; bestW = W; best_bps = bps; }
+  }
+  int W = env_int("SCDC_W", bestW);
+  if (W < 1 || W > 32 || per_warp * W > cap) W = bestW;
+  ScatterPlan pl;
+  pl.J = J; pl.W = W; pl.blocks_per_sm = best_bps; pl.smem = per_warp * W;
+  return pl;
+}
+
+template <int J>
+cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, cudaStream_t s) {
+  auto kern = scdc::k_scatter<J>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return e;
+  const int nCJ = Bpad / (32 * J);
+  dim3 grid(h->G, (nCJ + pl.W - 1) / pl.W);
+  kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, h->lab2.p, Bpad,
+                                        h->ngroup.p, h->gene_order.p, h->M2.p);
+  return cudaGetLastError();
+}
+
+int pick_batch(const scdc_handle* h, const scdc_options* o) {
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const double per_perm = (double)h->C * h->G * h->K * 8.0 + (double)h->N * 1.125 +
+                          ((o->perm_ct != nullptr) ? 2.0 * h->N : 0.0) +
+                          (o->return_distributions ? (double)h->R * ((h->C == 2) ? 3 : 1) * 8.0 : 0.0);
+  double budget = std::min((double)free_b * 0.5, 24.0e9);
+  long long B = (long long)(budget / per_perm);
+  B = std::min<long long>(B, 4096);
+  if (o->batch_size > 0) B = o->batch_size;
+  B = std::min<long long>(B, ((o->iterations + 127) / 128) * 128);
+  B = std::max<long long>(128, (B / 128) * 128);
+  return (int)B;
+}
+
+// Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
+// h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
+int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st) {
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K, R = h->R;
+  const int B = pick_batch(h, o);
+  const int Bw = B / 32;
+  const ScatterPlan pl = plan_scatter(h, B);
+  const bool uploaded = o->perm_ct != nullptr;
+  const int ncols_d = (C == 2) ? 3 : 1;
+  const size_t msz = (size_t)Bw * G * K * 32;
+  CU(h->lab2.ensure((size_t)N * B));
+  if (C == 2) { CU(h->bits1.ensure((size_t)N * Bw)); CU(h->M1.ensure(msz)); }
+  CU(h->M2.ensure(msz));
+  CU(h->counts.ensure((size_t)R * h->ncols + 1));
+  CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
+  if (uploaded) {
+    CU(h->up_ct.ensure((size_t)B * N));
+    if (C == 2) CU(h->up_cond.ensure((size_t)B * N));
+    CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
+  }
+  if (dist_host) CU(h->dist.ensure((size_t)B * ncols_d * R));
+  const int draw_threads = 32;
+  const size_t draw_smem = (size_t)((C == 2) ? 4 * T : T) * draw_threads * sizeof(uint32_t);
+  if (!uploaded && draw_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(scdc::k_draw_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)draw_smem));
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() -> cudaError_t {
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return rc;
+    evs.push_back(e);
+    return cudaEventRecord(e, s);
+  };
+  struct EvGuard {
+    std::vector<cudaEvent_t>& v;
+    ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
+  } guard{evs};
+  int64_t launches = 0, reduce_launches = 0;
+  double reduce_bytes = 0;
+  const double sv = 8.0;
+  for (int64_t done = 0; done < o->iterations; done += B) {
+    const int nb = (int)std::min<int64_t>(B, o->iterations - done);
+    CU(mark());
+    if (uploaded) {
+      CU(cudaMemcpyAsync(h->up_ct.p, o->perm_ct + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
+      if (C == 2)
+        CU(cudaMemcpyAsync(h->up_cond.p, o->perm_cond + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
+      scdc::k_check_uploaded<<<nb, 256, 2 * K * sizeof(int), s>>>(N, T, C, h->ct.p, h->up_cond.p, h->up_ct.p, h->expect.p,
+                                                                  h->flag.p);
+      dim3 grid((N + 31) / 32, B / 32), block(32, 32);
+      scdc::k_pack_uploaded<<<grid, block, 0, s>>>(N, T, C, nb, B, pl.J, h->ct.p, h->cond.p, h->up_cond.p, h->up_ct.p,
+                                                   h->bits1.p, h->lab2.p);
+      launches += 2;
+    } else {
+      scdc::k_draw_labels<<<B / draw_threads, draw_threads, draw_smem, s>>>(
+          N, T, C, h->ct.p, h->urn_init.p, o->seed, o->perm_offset + done, B, pl.J, h->bits1.p, h->lab2.p, nullptr, nullptr);
+      launches += 1;
+    }
+    CU(cudaGetLastError());
+    CU(mark());
+    if (C == 2) {
+      const int nWC = B / 128, W = 8;
+      const long long tasks = (long long)G * nWC;
+      scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, T, nWC, h->segptr.p, h->rowidx_s.p,
+                                                                           h->values_s.p, h->bits1.p, Bw, h->ngroup.p,
+                                                                           h->gene_order.p, h->M1.p);
+      CU(cudaGetLastError());
+      ++launches; ++reduce_launches;
+    }
+    cudaError_t le = (pl.J == 4) ? launch_scatter<4>(h, pl, B, s) : (pl.J == 2) ? launch_scatter<2>(h, pl, B, s)
+                                                                                : launch_scatter<1>(h, pl, B, s);
+    CU(le);
+    ++launches; ++reduce_launches;
+    // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
+    reduce_bytes += (double)C * ((double)h->nnz * (sv + 4.0) + 4.0 * (G + 1)) + (double)B * N * (C == 2 ? 1.125 : 1.0) +
+                    (double)C * B * K * G * sv;
+    CU(mark());
+    if (R > 0) {
+      scdc::ScoreArgs A;
+      A.R = R; A.G = G; A.T = T; A.C = C; A.nL = h->nL; A.nR = h->nR; A.ncols = h->ncols; A.score_type = o->score_type;
+      A.nChunks = (nb + 31) / 32; A.n_valid = nb;
+      A.sub_gene = h->sub_gene.p; A.row_lri = h->row_lri.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p;
+      A.obs = h->obs.p; A.M1 = h->M1.p; A.M2 = h->M2.p; A.counts = h->counts.p;
+      A.dist = dist_host ? h->dist.p : nullptr;
+      const int blocks = std::max(1, std::min((R + 7) / 8, h->num_sms * 8));
+      scdc::k_score_count<<<blocks, 256, 0, s>>>(A);
+      CU(cudaGetLastError());
+      ++launches;
+      if (dist_host)
+        CU(cudaMemcpyAsync(dist_host + (size_t)done * ncols_d * R, h->dist.p, (size_t)nb * ncols_d * R * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+    }
+    CU(mark());
+    if (uploaded || dist_host) CU(cudaStreamSynchronize(s));  // host source / destination buffers are reused per batch
+  }
+  CU(cudaStreamSynchronize(s));
+  if (uploaded) {
+    int flag = 0;
+    CU(cudaMemcpy(&flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag == 2) return fail(SCDC_EINVAL, "uploaded labels contain a code outside [0, n_conditions) x [0, n_celltypes)");
+    if (flag == 1)
+      return fail(SCDC_EINVAL,
+                  "uploaded labels do not preserve the number of cells per (cell type, condition): not a "
+                  "run_stat_iteration shuffle (reference R/utils_permutation.R:536-569)");
+  }
+  if (st) {
+    for (size_t i = 0; i + 3 < evs.size(); i += 4) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, evs[i], evs[i + 1]);
+      cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]);
+      cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
+      st->ms_labels += a; st->ms_reduce += b; st->ms_score += c;
+    }
+    st->reduce_bytes += reduce_bytes;
+    st->reduce_launches += reduce_launches;
+    st->kernel_launches += launches;
+    st->batch_size = B;
+  }
+  return SCDC_OK;
+}
+
+int finish_counts(const scdc_handle* h, const std::vector<long long>& raw, uint64_t* out) {
+  const size_t n = (size_t)h->R * h->ncols;
+  for (size_t i = 0; i < n; ++i) out[i] = h->obs_na[i] ? SCDC_COUNT_NA : (uint64_t)raw[i];
+  return SCDC_OK;
+}
+
+// ---- NCCL, loaded lazily (only the multi-GPU merge needs it) ------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
+    CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt64 = 4;  // ncclInt64
+constexpr int kNcclSum = 0;    // ncclSum
+
+}  // namespace
+
+extern "C" {
+
+int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
+  if (!h || !res) return fail(SCDC_EINVAL, "handle or result is NULL");
+  int rc = validate_options(nullptr, h->C, o);
+  if (rc) return rc;
+  if (!res->counts && !res->counts_device) return fail(SCDC_EINVAL, "result.counts and result.counts_device are both NULL");
+  if (o->return_distributions && !res->distributions)
+    return fail(SCDC_EINVAL, "return_distributions set but result.distributions is NULL");
+  const double t0 = now_ms();
+  memset(&res->stats, 0, sizeof res->stats);
+  rc = run_device(h, o, o->return_distributions ? res->distributions : nullptr, &res->stats);
+  if (rc) return rc;
+  const double t1 = now_ms();
+  const size_t n = (size_t)h->R * h->ncols;
+  if (res->counts_device && n) {
+    scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->counts.p, (long long*)res->counts_device);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    res->stats.kernel_launches += 1;
+  }
+  if (res->counts) {
+    std::vector<uint32_t> raw32(n);
+    if (n) CU(cudaMemcpy(raw32.data(), h->counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<long long> raw(raw32.begin(), raw32.end());
+    finish_counts(h, raw, res->counts);
+  }
+  res->stats.ms_merge = now_ms() - t1;
+  res->stats.ms_total = now_ms() - t0;
+  res->stats.n_gpus = 1;
+  return SCDC_OK;
+}
+
+int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* res) {
+  if (!res) return fail(SCDC_EINVAL, "result is NULL");
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  rc = validate_options(p, p->n_conditions, o);
+  if (rc) return rc;
+  if (!res->counts) return fail(SCDC_EINVAL, "result.counts is NULL");
+  if (o->return_distributions && !res->distributions)
+    return fail(SCDC_EINVAL, "return_distributions set but result.distributions is NULL");
+  std::vector<int> ids;
+  const int avail = count_sm100_devices(&ids);
+  if (avail == 0)
+    return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
+  if (o->n_gpus < 0) return fail(SCDC_EINVAL, "n_gpus must be >= 0");
+  int W = (o->n_gpus == 0) ? avail : o->n_gpus;
+  if (W > avail) return fail(SCDC_ENOGPU, "n_gpus = %d but only %d compute-capability-10.x devices are visible", W, avail);
+  if (o->return_distributions) W = 1;  // <= 1000 replicates (R/utils_permutation.R:103-109): single GPU
+  W = (int)std::min<int64_t>(W, std::max<int64_t>(1, o->iterations / 128));
+  const double t0 = now_ms();
+  memset(&res->stats, 0, sizeof res->stats);
+  if (W == 1) {
+    scdc_handle* h = nullptr;
+    rc = scdc_create(p, ids[0], &h);
+    if (rc) return rc;
+    scdc_result r1 = *res;
+    r1.counts_device = nullptr;
+    rc = scdc_run(h, o, &r1);
+    res->stats = r1.stats;
+    res->stats.ms_upload = h->ms_upload;
+    scdc_release(h);
+    res->stats.ms_total = now_ms() - t0;
+    return rc;
+  }
+  // ---- multi-GPU: replicate ranges sharded over W devices, one host thread per device ----
+  if (!g_nccl.load()) return fail(SCDC_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  std::vector<scdc_handle*> hs(W, nullptr);
+  std::vector<int> rcs(W, 0);
+  std::vector<std::string> errs(W);
+  std::vector<scdc_stats> sts(W);
+  std::vector<scdc_options> os(W, *o);
+  const int64_t per = (o->iterations + W - 1) / W;
+  {
+    std::vector<std::thread> th;
+    for (int r = 0; r < W; ++r) {
+      th.emplace_back([&, r]() {
+        memset(&sts[r], 0, sizeof(scdc_stats));
+        rcs[r] = scdc_create(p, ids[r], &hs[r]);
+        if (rcs[r]) { errs[r] = g_err; return; }
+        const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
+        os[r].iterations = e - b;
+        os[r].perm_offset = o->perm_offset + b;
+        if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
+        if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
+        if (os[r].iterations > 0) {
+          rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r]);
+          if (rcs[r]) errs[r] = g_err;
+        } else {
+          cudaSetDevice(hs[r]->device);
+          hs[r]->counts.ensure((size_t)hs[r]->R * hs[r]->ncols + 1);
+          cudaMemset(hs[r]->counts.p, 0, ((size_t)hs[r]->R * hs[r]->ncols + 1) * sizeof(uint32_t));
+        }
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  auto cleanup = [&]() { for (auto h : hs) scdc_release(h); };
+  for (int r = 0; r < W; ++r)
+    if (rcs[r]) { g_err = errs[r]; cleanup(); return rcs[r]; }
+  const double t1 = now_ms();
+  const size_t n = (size_t)p->n_rows * hs[0]->ncols;
+  std::vector<DBuf<long long>> wide(W);
+  std::vector<void*> comms(W, nullptr);
+  std::vector<int> devs(ids.begin(), ids.begin() + W);
+  int nrc = g_nccl.CommInitAll(comms.data(), W, devs.data());
+  if (nrc != 0) { cleanup(); return fail(SCDC_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); }
+  int bad = 0;
+  for (int r = 0; r < W && !bad; ++r) {
+    cudaSetDevice(hs[r]->device);
+    if (wide[r].alloc(n + 1) != cudaSuccess) { bad = 1; break; }
+    if (n) scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, hs[r]->stream>>>(n, hs[r]->counts.p, wide[r].p);
+  }
+  if (!bad && n) {
+    g_nccl.GroupStart();
+    for (int r = 0; r < W; ++r) {
+      nrc = g_nccl.AllReduce(wide[r].p, wide[r].p, n, kNcclInt64, kNcclSum, comms[r], hs[r]->stream);
+      if (nrc != 0) bad = 2;
+    }
+    nrc = g_nccl.GroupEnd();
+    if (nrc != 0) bad = 2;
+  }
+  for (int r = 0; r < W; ++r) {
+    cudaSetDevice(hs[r]->device);
+    if (cudaStreamSynchronize(hs[r]->stream) != cudaSuccess) bad = bad ? bad : 3;
+  }
+  std::vector<long long> raw(n);
+  if (!bad && n) {
+    cudaSetDevice(hs[0]->device);
+    if (cudaMemcpy(raw.data(), wide[0].p, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) bad = 3;
+  }
+  for (int r = 0; r < W; ++r) if (comms[r]) g_nccl.CommDestroy(comms[r]);
+  if (bad) {
+    for (auto& w : wide) { w.release(); }
+    cleanup();
+    return fail(bad == 1 ? SCDC_ENOMEM : bad == 2 ? SCDC_ENCCL : SCDC_ECUDA, "counter merge across %d GPUs failed (stage %d)", W, bad);
+  }
+  finish_counts(hs[0], raw, res->counts);
+  for (int r = 0; r < W; ++r) {
+    res->stats.ms_labels = std::max(res->stats.ms_labels, sts[r].ms_labels);
+    res->stats.ms_reduce = std::max(res->stats.ms_reduce, sts[r].ms_reduce);
+    res->stats.ms_score = std::max(res->stats.ms_score, sts[r].ms_score);
+    res->stats.ms_upload = std::max(res->stats.ms_upload, hs[r]->ms_upload);
+    res->stats.reduce_bytes += sts[r].reduce_bytes;
+    res->stats.reduce_launches += sts[r].reduce_launches;
+    res->stats.kernel_launches += sts[r].kernel_launches + 1;
+    res->stats.batch_size = sts[r].batch_size;
+  }
+  for (int r = 0; r < W; ++r) { cudaSetDevice(hs[r]->device); wide[r].release(); }
+  cleanup();
+  res->stats.ms_merge = now_ms() - t1;
+  res->stats.ms_total = now_ms() - t0;
+  res->stats.n_gpus = W;
+  return SCDC_OK;
+}
+
+int scdc_group_means(scdc_handle* h, double* means, double* detection_rate) {
+  if (!h) return fail(SCDC_EINVAL, "handle is NULL");
+  CU(cudaSetDevice(h->device));
+  DBuf<double> out;
+  const size_t n = (size_t)h->K * h->G;
+  CU(out.alloc(n));
+  for (int mode = 0; mode < 2; ++mode) {
+    double* dst = mode == 0 ? means : detection_rate;
+    if (!dst) continue;
+    scdc::k_group_means<<<(h->G + 127) / 128, 128, 0, h->stream>>>(h->G, h->K, h->T, h->colptr.p, h->rowidx.p, h->values.p,
+                                                                 h->ct.p, h->C == 2 ? h->cond.p : nullptr, h->ngroup.p, mode,
+                                                                 out.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return SCDC_OK;
+}
+
+int scdc_draw_labels(scdc_handle* h, uint64_t seed, int64_t perm_offset, int64_t n, uint8_t* cond_out, uint8_t* ct_out) {
+  if (!h || !ct_out) return fail(SCDC_EINVAL, "handle or ct_out is NULL");
+  if (n < 1 || perm_offset < 0) return fail(SCDC_EINVAL, "n must be >= 1 and perm_offset >= 0");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int N = h->N, T = h->T, C = h->C;
+  const int B = 128;
+  DBuf<uint8_t> lab2, dct, dcond;
+  DBuf<uint32_t> bits1;
+  CU(lab2.alloc((size_t)N * B));
+  CU(bits1.alloc((size_t)N * (B / 32)));
+  CU(dct.alloc((size_t)B * N));
+  CU(dcond.alloc((size_t)B * N));
+  const int nt = 32;
+  const size_t smem = (size_t)((C == 2) ? 4 * T : T) * nt * sizeof(uint32_t);
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(scdc::k_draw_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int64_t done = 0; done < n; done += B) {
+    const int nb = (int)std::min<int64_t>(B, n - done);
+    scdc::k_draw_labels<<<B / nt, nt, smem, s>>>(N, T, C, h->ct.p, h->urn_init.p, seed, perm_offset + done, B, 1, bits1.p,
+                                                  lab2.p, dcond.p, dct.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ct_out + (size_t)done * N, dct.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));
+    if (cond_out && C == 2)
+      CU(cudaMemcpyAsync(cond_out + (size_t)done * N, dcond.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return SCDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// scdc_kernels.cuh — sm_100a kernels of the permutation-test hot path (see DESIGN.md for the data layout).
+//
+//   K1  k_draw_labels      on-device Philox4x32-10 label shuffles          (replaces base::sample at
+//                                                                            reference R/utils_permutation.R:509,536-541,552-569)
+//   K1u k_pack_uploaded    validation mode: re-layout uploaded label matrices
+//   K2a k_pass1_cond       differential pass 1 (conditions shuffled inside fixed cell types): register accumulators
+//   K2b k_scatter<J>       general segmented sum over CSC, lane = replicate, shared-memory accumulators
+//                          (replaces DelayedArray::rowsum + "/ table(group)", reference R/utils_cci.R:441-462)
+//   K3  k_score_count      gather + complex-min + score + diff + `>=` compare + counter bump
+//                          (replaces build_cci_or_drate("cci"), reference R/utils_cci.R:464-712, the column assembly
+//                          of R/utils_permutation.R:579-602 and the counting of R/utils_permutation.R:139-211)
+//
+// Exactness contract: every (gene, group) sum is accumulated in fp64 by ONE lane walking the gene column in ascending
+// cell order — the order of the C loop behind rowsum — so means, scores and therefore exceedance counts are bit-identical
+// to the CPU oracle for the same labels. Compile with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scdc {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11). counter = (draw block j, 0, replicate lo, replicate hi), key = seed.
+// ------------------------------------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t c0, c1, c2, c3, k0, k1;
+  uint32_t out[4];
+  int have;
+  __host__ __device__ Philox(uint64_t seed, uint64_t replicate)
+      : c0(0), c1(0), c2((uint32_t)replicate), c3((uint32_t)(replicate >> 32)), k0((uint32_t)seed),
+        k1((uint32_t)(seed >> 32)), have(0) {}
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ inline void refill() {
+    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, x0, hi0, lo0);
+      mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+      uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+    have = 4;
+    if (++c0 == 0) ++c1;
+  }
+  __host__ __device__ inline uint32_t next() {
+    if (have == 0) refill();
+    uint32_t v = out[4 - have];  // consumed in order out[0..3]
+    --have;
+    return v;
+  }
+  // uniform integer in [0, range), range >= 1; Lemire's multiply-shift with rejection (exactly unbiased)
+  __host__ __device__ inline uint32_t bounded(uint32_t range) {
+    uint64_t m = (uint64_t)next() * range;
+    uint32_t l = (uint32_t)m;
+    if (l < range) {
+      uint32_t t = (0u - range) % range;
+      while (l < t) {
+        m = (uint64_t)next() * range;
+        l = (uint32_t)m;
+      }
+    }
+    return (uint32_t)(m >> 32);
+  }
+};
+
+// byte offset of replicate q's label inside one cell's label row (row length Bpad bytes), J replicates per lane
+__host__ __device__ inline int lab2_offset(int q, int J) {
+  int chunk = q / (32 * J), r = q % (32 * J);
+  return chunk * 32 * J + (r % 32) * J + r / 32;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: one thread = one replicate; sequential urn draws over the cells (a uniformly random arrangement of a multiset
+// revealed cell by cell: next label k with probability remaining[k] / remaining total). Fenwick trees live in shared
+// memory, laid out [node][thread] so a warp never bank-conflicts.
+//   detection   : ct' = global shuffle of cell types                    (R/utils_permutation.R:509)
+//   differential: cond' = shuffle of conditions inside each cell type   (:536-541)
+//                 ct'   = shuffle of cell types inside each cond' class (:552-569)
+// outputs: bits1[cell][Bpad/32] (bit q%32 of word q/32 = cond' of replicate q), lab2[cell][Bpad] (group code
+// cond' * T + ct' in the K2b layout). Optional row-major debug copies for scdc_draw_labels.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_draw_labels(int N, int T, int C, const uint8_t* __restrict__ ct, const uint32_t* __restrict__ init,
+                              uint64_t seed, int64_t perm0, int Bpad, int J, uint32_t* __restrict__ bits1,
+                              uint8_t* __restrict__ lab2, uint8_t* __restrict__ dbg_cond, uint8_t* __restrict__ dbg_ct) {
+  extern __shared__ uint32_t sm_u32[];
+  const int nt = blockDim.x, tx = threadIdx.x;
+  const int q = blockIdx.x * nt + tx;  // replicate inside the batch (always < Bpad: Bpad % blockDim == 0)
+  // state rows: differential: rem[c][t] (2T rows) then tree[c][1..T] (2T rows) ; detection: tree[1..T] (T rows)
+  const int n_state = (C == 2) ? 4 * T : T;
+  for (int i = 0; i < n_state; ++i) sm_u32[i * nt + tx] = init[i];
+  uint32_t tot2[2] = {init[n_state], init[n_state + 1]};
+#define ST(i) sm_u32[(i) * nt + tx]
+  Philox rng(seed, (uint64_t)(perm0 + q));
+  int top = 1;
+  while (top * 2 <= T) top *= 2;
+  const int Bw = Bpad / 32;
+  const int off2 = lab2_offset(q, J);
+  for (int i = 0; i < N; ++i) {
+    int c = 0;
+    int tree0 = 0;  // first row of the Fenwick tree to draw from
+    if (C == 2) {
+      int t = ct[i];
+      uint32_t r0 = ST(t), r1 = ST(T + t);
+      uint32_t u = rng.bounded(r0 + r1);
+      c = (u < r0) ? 0 : 1;
+      ST(c * T + t) -= 1;
+      tree0 = 2 * T + c * T;
+    }
+    uint32_t u = rng.bounded(tot2[c]);
+    tot2[c] -= 1;
+    int pos = 0;
+    for (int step = top; step > 0; step >>= 1) {
+      int nxt = pos + step;
+      if (nxt <= T) {
+        uint32_t w = ST(tree0 + nxt - 1);
+        if (w <= u) { pos = nxt; u -= w; }
+      }
+    }
+    for (int k = pos + 1; k <= T; k += k & (-k)) ST(tree0 + k - 1) -= 1;
+    if (C == 2) {
+      uint32_t word = __ballot_sync(0xffffffffu, c == 1);
+      if ((tx & 31) == 0) bits1[(size_t)i * Bw + (q >> 5)] = word;
+    }
+    lab2[(size_t)i * Bpad + off2] = (uint8_t)(c * T + pos);
+    if (dbg_ct) dbg_ct[(size_t)q * N + i] = (uint8_t)pos;
+    if (dbg_cond) dbg_cond[(size_t)q * N + i] = (uint8_t)c;
+  }
+#undef ST
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1u: validation mode. up_ct / up_cond are replicate-major [nb][N]; writes the same device layouts as K1.
+// Replicates q >= nb (padding) get the original labels (results for them are never counted).
+// grid = (ceil(N/32), Bpad/32), block = (32, 32): threadIdx.x = replicate in word, threadIdx.y = cell in tile.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_pack_uploaded(int N, int T, int C, int nb, int Bpad, int J, const uint8_t* __restrict__ ct,
+                                const uint8_t* __restrict__ cond, const uint8_t* __restrict__ up_cond,
+                                const uint8_t* __restrict__ up_ct, uint32_t* __restrict__ bits1,
+                                uint8_t* __restrict__ lab2) {
+  __shared__ uint8_t tile_ct[32][33], tile_cd[32][33];
+  const int cell0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  {  // load: threadIdx.x walks cells (coalesced), threadIdx.y walks replicates
+    int cell = cell0 + threadIdx.x, q = q0 + threadIdx.y;
+    uint8_t vct = 0, vcd = 0;
+    if (cell < N) {
+      if (q < nb) {
+        vct = up_ct[(size_t)q * N + cell];
+        vcd = (C == 2) ? up_cond[(size_t)q * N + cell] : 0;
+      } else {
+        vct = ct[cell];
+        vcd = (C == 2) ? cond[cell] : 0;
+      }
+    }
+    tile_ct[threadIdx.y][threadIdx.x] = vct;
+    tile_cd[threadIdx.y][threadIdx.x] = vcd;
+  }
+  __syncthreads();
+  int cell = cell0 + threadIdx.y, q = q0 + threadIdx.x;
+  uint8_t vct = tile_ct[threadIdx.x][threadIdx.y], vcd = tile_cd[threadIdx.x][threadIdx.y];
+  uint32_t word = __ballot_sync(0xffffffffu, vcd == 1);
+  if (cell < N) {
+    if (C == 2 && threadIdx.x == 0) bits1[(size_t)cell * (Bpad / 32) + (q >> 5)] = word;
+    lab2[(size_t)cell * Bpad + lab2_offset(q, J)] = (uint8_t)(vcd * T + vct);
+  }
+}
+
+// validation of uploaded labels: every replicate must keep n(cell type, condition) of both passes
+// (R/utils_permutation.R:536-569 guarantees it). One block per replicate. flag[0] != 0 on violation or bad code.
+__global__ void k_check_uploaded(int N, int T, int C, const uint8_t* __restrict__ ct, const uint8_t* __restrict__ up_cond,
+                                 const uint8_t* __restrict__ up_ct, const uint32_t* __restrict__ expect /*[C*T]*/,
+                                 int* __restrict__ flag) {
+  extern __shared__ int hist[];  // [2][C*T]
+  const int K = C * T, q = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int c = (C == 2) ? up_cond[(size_t)q * N + i] : 0;
+    int t2 = up_ct[(size_t)q * N + i];
+    if (c >= C || t2 >= T) { atomicExch(flag, 2); continue; }
+    atomicAdd(&hist[c * T + ct[i]], 1);       // pass 1 groups: (cond', original cell type)
+    atomicAdd(&hist[K + c * T + t2], 1);      // pass 2 groups: (cond', ct')
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x)
+    if ((uint32_t)hist[i] != expect[i % K]) atomicExch(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// staging helper: a warp loads 32 consecutive (cell, value) entries coalesced and re-reads them one by one as a
+// 16-byte broadcast from shared memory (1 wavefront per entry instead of 3 shuffles).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pack_entry(int cell, double v) {
+  long long b = __double_as_longlong(v);
+  return make_uint4((uint32_t)cell, 0u, (uint32_t)b, (uint32_t)(b >> 32));
+}
+__device__ __forceinline__ double entry_value(const uint4& e) {
+  return __longlong_as_double((long long)(((unsigned long long)e.w << 32) | e.z));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2a: differential pass 1. Cell types are fixed, only the condition bit varies per replicate, so the entries of a
+// gene column, pre-sorted by (cell type, cell) [stable: ascending cell order inside every (cell type, cond') group is
+// kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 128 replicates
+// (4 per lane): one uniform 16-byte load brings the condition bits of a cell for all 128.
+// M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
+// grid.x = G * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pass1_cond(int G, int T, int nWC, const int* __restrict__ segptr,
+                                                    const int* __restrict__ rowidx_s, const double* __restrict__ values_s,
+                                                    const uint32_t* __restrict__ bits1, int Bw,
+                                                    const double* __restrict__ ngroup, const int* __restrict__ gene_order,
+                                                    double* __restrict__ M1) {
+  __shared__ uint4 stage_all[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const long long task = (long long)blockIdx.x * W + warp;
+  if (task >= (long long)G * nWC) return;
+  const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
+  uint4* stage = stage_all[warp];
+  const int K = 2 * T;
+  const int* sp = segptr + (size_t)g * (T + 1);
+  for (int t = 0; t < T; ++t) {
+    const int beg = sp[t], end = sp[t + 1];
+    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int e0 = beg; e0 < end; e0 += 32) {
+      int e = e0 + lane;
+      int cell = 0;
+      double v = 0.0;
+      if (e < end) { cell = rowidx_s[e]; v = values_s[e]; }
+      __syncwarp();
+      stage[lane] = pack_entry(cell, v);
+      __syncwarp();
+      const int n = min(32, end - e0);
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        uint4 en = stage[i];
+        double val = entry_value(en);
+        uint4 w = *reinterpret_cast<const uint4*>(bits1 + (size_t)en.x * Bw + wc * 4);
+        uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((ww[j] >> lane) & 1u) a1[j] += val; else a0[j] += val;
+        }
+      }
+    }
+    const double n0 = ngroup[t], n1 = ngroup[T + t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      size_t base = (((size_t)(wc * 4 + j) * G + g) * K) * 32 + lane;
+      M1[base + (size_t)t * 32] = a0[j] / n0;
+      M1[base + (size_t)(T + t) * 32] = a1[j] / n1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2b: general segmented sum. One warp = one gene column x (32*J) replicates; lane owns J replicates and walks the
+// column in ascending cell order doing acc[label][j][lane] += x in shared memory (fp64). The accumulator row stride
+// is a multiple of 32 banks and the column index is the lane, so the read-modify-write is conflict-free and needs no
+// atomics whatever the labels are. lab2 layout: [cell][Bpad] bytes, lane's J labels adjacent (one J-byte load).
+// M2 layout: [chunk32][gene][k][32 lanes], value = sum / n_k.
+// grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K*J*32*8 + 512).
+// ------------------------------------------------------------------------------------------------------------------
+template <int J> struct LabWord;
+template <> struct LabWord<1> { typedef uint8_t type; };
+template <> struct LabWord<2> { typedef uint16_t type; };
+template <> struct LabWord<4> { typedef uint32_t type; };
+
+template <int J>
+__global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                          const double* __restrict__ values, const uint8_t* __restrict__ lab2, int Bpad,
+                          const double* __restrict__ ngroup, const int* __restrict__ gene_order, double* __restrict__ M2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef typename LabWord<J>::type lab_t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int cJ = blockIdx.y * W + warp;
+  if (cJ >= nCJ) return;
+  const int g = gene_order[blockIdx.x];
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw) + warp * 32;
+  double* acc = reinterpret_cast<double*>(smem_raw + (size_t)W * 512) + (size_t)warp * K * J * 32 + lane;
+  for (int i = 0; i < K * J; ++i) acc[i * 32] = 0.0;
+  const int beg = colptr[g], end = colptr[g + 1];
+  const uint8_t* labbase = lab2 + (size_t)cJ * 32 * J + lane * J;
+  constexpr int U = 4;
+  int cell_n = 0;
+  double v_n = 0.0;
+  if (beg + lane < end) { cell_n = rowidx[beg + lane]; v_n = values[beg + lane]; }
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    __syncwarp();
+    stage[lane] = pack_entry(cell_n, v_n);
+    __syncwarp();
+    {  // prefetch the next 32 entries while this stage is consumed; padding entries add +0.0 to cell 0's group
+      int e = e0 + 32 + lane;
+      cell_n = 0;
+      v_n = 0.0;
+      if (e < end) { cell_n = rowidx[e]; v_n = values[e]; }
+    }
+#pragma unroll 1
+    for (int i = 0; i < 32; i += U) {
+      uint4 en[U];
+      lab_t lb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) en[u] = stage[i + u];
+#pragma unroll
+      for (int u = 0; u < U; ++u) lb[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en[u].x * Bpad);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double val = entry_value(en[u]);
+        double cur[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) cur[j] = acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val;
+      }
+    }
+  }
+  __syncwarp();
+  for (int k = 0; k < K; ++k) {
+    const double nk = ngroup[k];
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      M2[(((size_t)(cJ * J + j) * G + g) * K + k) * 32 + lane] = acc[(k * J + j) * 32] / nk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3 (v1, generic): one warp = one tested row, lane = replicate, loop over the batch's 32-replicate chunks.
+// Reads the group means coalesced ([chunk][gene][k][lane]), forms the reference's per-iteration columns
+//   differential: [cond2-cond1 score (pass 1), cond1 score (pass 2), cond2 score (pass 2), L_i diffs, R_j diffs (pass 1)]
+//   detection   : [score]
+// compares with the observed values (`>=`; two-sided abs() for DE and subunit columns) and adds ballots to the row's
+// counters. A row is owned by exactly one warp per launch, so the counter update is a plain add.
+// ------------------------------------------------------------------------------------------------------------------
+struct ScoreArgs {
+  int R, G, T, C, nL, nR, ncols, score_type;
+  int nChunks;      // 32-replicate chunks in this batch
+  int n_valid;      // replicates of this batch that count
+  const int* sub_gene;   // [L][nL+nR]
+  const int* row_lri;
+  const int* row_emit;
+  const int* row_recv;
+  const double* obs;     // column-major [R][ncols]
+  const double* M1;      // pass-1 means (differential) or nullptr
+  const double* M2;      // pass-2 means / detection means
+  uint32_t* counts;      // column-major [R][ncols]
+  double* dist;          // nullptr or [n_valid][ncols_d][R] (this batch's slice)
+};
+
+__device__ __forceinline__ double score_of(double a, double b, int score_type) {
+  return score_type == 0 ? sqrt(a * b) : (a + b) / 2;
+}
+
+__global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int K = A.C * A.T, nS = A.nL + A.nR;
+  const int ncols_d = (A.C == 2) ? 3 : 1;
+  for (int row = warp_global; row < A.R; row += n_warps) {
+    const int l = A.row_lri[row], e = A.row_emit[row], r = A.row_recv[row];
+    int gs[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) gs[s] = (s < nS) ? A.sub_gene[l * nS + s] : -1;
+    double ob[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ob[c] = (c < A.ncols) ? A.obs[(size_t)c * A.R + row] : 0.0;
+    uint32_t cnt[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) cnt[c] = 0;
+    for (int ch = 0; ch < A.nChunks; ++ch) {
+      const bool valid = (ch * 32 + lane) < A.n_valid;
+      const size_t cb = (size_t)ch * A.G;
+      if (A.C == 1) {
+        double mL = 0.0, mR = 0.0;
+        bool hL = false, hR = false;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < nS && gs[s] >= 0) {
+            const bool isL = s < A.nL;
+            double v = A.M2[((cb + gs[s]) * K + (isL ? e : r)) * 32 + lane];
+            if (isL) { mL = hL ? fmin(mL, v) : v; hL = true; } else { mR = hR ? fmin(mR, v) : v; hR = true; }
+          }
+        }
+        double sc = score_of(mL, mR, A.score_type);
+        uint32_t b = __ballot_sync(0xffffffffu, valid && (sc >= ob[0]));
+        cnt[0] += __popc(b);
+        if (A.dist && valid) A.dist[((size_t)(ch * 32 + lane) * ncols_d) * A.R + row] = sc;
+      } else {
+        double s1[2], s2[2];
+        double dsub[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) dsub[s] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double mL = 0.0, mR = 0.0, qL = 0.0, qR = 0.0;
+          bool hL = false, hR = false;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < nS && gs[s] >= 0) {
+              const bool isL = s < A.nL;
+              const size_t idx = ((cb + gs[s]) * K + c * A.T + (isL ? e : r)) * 32 + lane;
+              double v1 = A.M1[idx], v2 = A.M2[idx];
+              dsub[s] = (c == 0) ? v1 : (v1 - dsub[s]);  // cond2 - cond1 (R/utils_cci.R:212-239)
+              if (isL) {
+                mL = hL ? fmin(mL, v1) : v1; qL = hL ? fmin(qL, v2) : v2; hL = true;
+              } else {
+                mR = hR ? fmin(mR, v1) : v1; qR = hR ? fmin(qR, v2) : v2; hR = true;
+              }
+            }
+          }
+          s1[c] = score_of(mL, mR, A.score_type);
+          s2[c] = score_of(qL, qR, A.score_type);
+        }
+        const double de = s1[1] - s1[0];
+        cnt[0] += __popc(__ballot_sync(0xffffffffu, valid && (fabs(de) >= fabs(ob[0]))));
+        cnt[1] += __popc(__ballot_sync(0xffffffffu, valid && (s2[0] >= ob[1])));
+        cnt[2] += __popc(__ballot_sync(0xffffffffu, valid && (s2[1] >= ob[2])));
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < nS) cnt[3 + s] += __popc(__ballot_sync(0xffffffffu, valid && gs[s] >= 0 && (fabs(dsub[s]) >= fabs(ob[3 + s]))));
+        }
+        if (A.dist && valid) {
+          double* d = A.dist + ((size_t)(ch * 32 + lane) * 3) * A.R + row;
+          d[0] = de;
+          d[(size_t)A.R] = s2[0];
+          d[(size_t)2 * A.R] = s2[1];
+        }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < A.ncols) A.counts[(size_t)c * A.R + row] += cnt[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Observed-pass helper (aggregate_cells on the original labels): one thread per gene, sequential over the column.
+// out is column-major [K][G]: out[g*K + k]. mode 0: sum of x ; mode 1: sum of 1*(x > 0).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_group_means(int G, int K, int T, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                              const double* __restrict__ values, const uint8_t* __restrict__ ct,
+                              const uint8_t* __restrict__ cond, const double* __restrict__ ngroup, int mode,
+                              double* __restrict__ out) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double* o = out + (size_t)g * K;
+  for (int k = 0; k < K; ++k) o[k] = 0.0;
+  for (int e = colptr[g]; e < colptr[g + 1]; ++e) {
+    int cell = rowidx[e];
+    int k = (cond ? cond[cell] * T : 0) + ct[cell];
+    double v = values[e];
+    o[k] += (mode == 0) ? v : ((v > 0) ? 1.0 : 0.0);
+  }
+  for (int k = 0; k < K; ++k) o[k] = o[k] / ngroup[k];
+}
+
+__global__ void k_widen_counts(size_t n, const uint32_t* __restrict__ in, long long* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (long long)in[i];
+}
+
+}  // namespace scdc

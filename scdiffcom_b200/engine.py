@@ -1,0 +1,209 @@
+"""Thin object layer over the C-ABI: marshals integer-coded NumPy arrays into `scdc_problem` and runs the B200 engine.
+
+The arrays are exactly what SURVEY.md section 8b says the R glue passes through `.Call` (see include/scdc.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import Options, Problem, Result, ScdcError, check  # noqa: F401
+
+SCORE_TYPES = {"geometric_mean": 0, "arithmetic_mean": 1}
+
+
+def _arr(x, dtype):
+    if x is None:
+        return None
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class PermutationProblem:
+    """analysis_inputs + sub_cci_template_iter + observed vectors, integer-encoded (include/scdc.h: scdc_problem)."""
+    n_cells: int
+    n_genes: int
+    n_celltypes: int
+    n_conditions: int
+    max_nL: int
+    max_nR: int
+    colptr: np.ndarray      # int32 [G+1]
+    rowidx: np.ndarray      # int32 [nnz]
+    values: np.ndarray      # float64 [nnz]
+    ct_code: np.ndarray     # int32 [N]
+    cond_code: np.ndarray | None  # int32 [N] or None (detection mode)
+    sub_gene: np.ndarray    # int32 [L, nL+nR], -1 = NA
+    row_lri: np.ndarray     # int32 [R_sub]
+    row_emit: np.ndarray
+    row_recv: np.ndarray
+    observed: np.ndarray    # float64 [R_sub, ncols] (any layout; passed column-major)
+    _keep: list = field(default_factory=list, repr=False)
+
+    @property
+    def n_rows(self):
+        return int(self.row_lri.shape[0])
+
+    @property
+    def n_lri(self):
+        return int(self.sub_gene.shape[0])
+
+    @property
+    def ncols(self):
+        return 1 if self.n_conditions == 1 else 3 + self.max_nL + self.max_nR
+
+    @property
+    def nnz(self):
+        return int(self.colptr[-1])
+
+    def c_struct(self) -> Problem:
+        self.colptr = _arr(self.colptr, np.int32)
+        self.rowidx = _arr(self.rowidx, np.int32)
+        self.values = _arr(self.values, np.float64)
+        self.ct_code = _arr(self.ct_code, np.int32)
+        self.cond_code = _arr(self.cond_code, np.int32)
+        self.sub_gene = _arr(np.asarray(self.sub_gene).reshape(-1, self.max_nL + self.max_nR), np.int32)
+        self.row_lri = _arr(self.row_lri, np.int32)
+        self.row_emit = _arr(self.row_emit, np.int32)
+        self.row_recv = _arr(self.row_recv, np.int32)
+        obs = np.asarray(self.observed, dtype=np.float64).reshape(self.n_rows, self.ncols)
+        obs_f = np.asfortranarray(obs)
+        self._keep = [obs_f]
+        p = Problem()
+        p.n_cells, p.n_genes, p.n_celltypes, p.n_conditions = self.n_cells, self.n_genes, self.n_celltypes, self.n_conditions
+        p.n_lri, p.n_rows, p.max_nL, p.max_nR = self.n_lri, self.n_rows, self.max_nL, self.max_nR
+        p.colptr, p.rowidx, p.values = _ptr(self.colptr), _ptr(self.rowidx), _ptr(self.values)
+        p.ct_code, p.cond_code, p.sub_gene = _ptr(self.ct_code), _ptr(self.cond_code), _ptr(self.sub_gene)
+        p.row_lri, p.row_emit, p.row_recv = _ptr(self.row_lri), _ptr(self.row_emit), _ptr(self.row_recv)
+        p.observed = _ptr(obs_f)
+        return p
+
+
+def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
+             n_cells, keep):
+    o = Options()
+    o.iterations = int(iterations)
+    o.seed = int(seed) & (2**64 - 1)
+    o.perm_offset = int(perm_offset)
+    o.score_type = SCORE_TYPES[score_type] if isinstance(score_type, str) else int(score_type)
+    o.n_gpus = int(n_gpus)
+    o.precision = 0
+    o.batch_size = int(batch_size)
+    for name, lab in (("perm_cond", perm_cond), ("perm_ct", perm_ct)):
+        if lab is not None:
+            a = np.ascontiguousarray(lab, dtype=np.uint8)
+            if a.shape != (int(iterations), n_cells):
+                raise ValueError(f"{name} must have shape (iterations, n_cells) = ({iterations}, {n_cells}), got {a.shape}")
+            keep.append(a)
+            setattr(o, name, _ptr(a))
+    o.return_distributions = 1 if return_distributions else 0
+    return o
+
+
+def _finish(problem, counts_f, dist, stats):
+    counts = counts_f.astype(np.float64)
+    counts[counts_f == np.uint64(_lib.SCDC_COUNT_NA)] = np.nan
+    return {"counts": counts, "counts_raw": counts_f, "distributions": dist, "stats": stats.as_dict()}
+
+
+def device_count() -> int:
+    return int(_lib.load().scdc_device_count())
+
+
+def version() -> str:
+    return _lib.load().scdc_version().decode()
+
+
+def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="geometric_mean", n_gpus=1, perm_offset=0,
+                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False):
+    """One-shot `scdc_perm_counts` with HOST buffers (what the `.Call` wrapper does). Returns dict(counts [R_sub, ncols]
+    float64 with NaN = NA, distributions or None, stats)."""
+    lib = _lib.load()
+    keep = []
+    p = problem.c_struct()
+    o = _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
+                 problem.n_cells, keep)
+    counts = np.zeros((problem.n_rows, problem.ncols), dtype=np.uint64, order="F")
+    res = Result()
+    res.counts = _ptr(counts)
+    dist = None
+    if return_distributions:
+        ncd = 3 if problem.n_conditions == 2 else 1
+        dist = np.zeros((int(iterations), ncd, problem.n_rows), dtype=np.float64)
+        res.distributions = _ptr(dist)
+    check(lib.scdc_perm_counts(C.byref(p), C.byref(o), C.byref(res)))
+    return _finish(problem, counts, dist, res.stats)
+
+
+class Engine:
+    """Handle API: the problem stays resident in HBM on one device across runs (`scdc_create` / `scdc_run`)."""
+
+    def __init__(self, problem: PermutationProblem, device: int = -1):
+        self._lib = _lib.load()
+        self.problem = problem
+        self._h = C.c_void_p()
+        p = problem.c_struct()
+        check(self._lib.scdc_create(C.byref(p), int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.scdc_release(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, iterations, seed=42, score_type="geometric_mean", perm_offset=0, batch_size=0, perm_cond=None,
+            perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True):
+        keep = []
+        pr = self.problem
+        o = _options(iterations, seed, score_type, perm_offset, 1, batch_size, perm_cond, perm_ct, return_distributions,
+                     pr.n_cells, keep)
+        res = Result()
+        counts = None
+        if want_host_counts:
+            counts = np.zeros((pr.n_rows, pr.ncols), dtype=np.uint64, order="F")
+            res.counts = _ptr(counts)
+        if counts_device_ptr is not None:
+            res.counts_device = C.c_void_p(int(counts_device_ptr))
+        dist = None
+        if return_distributions:
+            ncd = 3 if pr.n_conditions == 2 else 1
+            dist = np.zeros((int(iterations), ncd, pr.n_rows), dtype=np.float64)
+            res.distributions = _ptr(dist)
+        check(self._lib.scdc_run(self._h, C.byref(o), C.byref(res)))
+        if counts is None:
+            return {"counts": None, "distributions": dist, "stats": res.stats.as_dict()}
+        return _finish(pr, counts, dist, res.stats)
+
+    def group_means(self, detection_rate=False):
+        """aggregate_cells on the original labels (R/utils_cci.R:441-462): [K, G] means (and detection rates)."""
+        pr = self.problem
+        K = pr.n_conditions * pr.n_celltypes
+        means = np.zeros((K, pr.n_genes), dtype=np.float64, order="F")
+        dr = np.zeros((K, pr.n_genes), dtype=np.float64, order="F") if detection_rate else None
+        check(self._lib.scdc_group_means(self._h, _ptr(means), _ptr(dr)))
+        return (means, dr) if detection_rate else means
+
+    def draw_labels(self, n, seed=42, perm_offset=0):
+        """The label matrices the device generator produces for replicates [perm_offset, perm_offset + n)."""
+        pr = self.problem
+        ct = np.zeros((int(n), pr.n_cells), dtype=np.uint8)
+        cond = np.zeros((int(n), pr.n_cells), dtype=np.uint8) if pr.n_conditions == 2 else None
+        check(self._lib.scdc_draw_labels(self._h, int(seed) & (2**64 - 1), int(perm_offset), int(n), _ptr(cond), _ptr(ct)))
+        return cond, ct

@@ -1,0 +1,148 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200): the CUDA path, called through the C-ABI, against the CPU oracle
+on the same inputs. Integer counts must be bit-exact; per-replicate fp64 values must be bit-exact too (same summation
+order, IEEE /, *, sqrt), which is stricter than north_star's 1e-5 relative tolerance."""
+import numpy as np
+import pytest
+
+from oracle import oracle_c
+from scdiffcom_b200 import Engine, perm_counts, run_stat_analysis, synthetic
+from scdiffcom_b200 import _lib
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+ST = {"geometric_mean": 0, "arithmetic_mean": 1}
+
+
+def _check_uploaded(prob, n, seed, score_type="geometric_mean", batch_size=0, dist=False):
+    pcond, pct = helpers.reference_like_labels(prob, n, seed)
+    want, want_d = oracle_c.perm_counts(prob, pct, pcond, score_type=ST[score_type], return_distributions=dist)
+    got = perm_counts(prob, n, score_type=score_type, perm_cond=pcond, perm_ct=pct, batch_size=batch_size,
+                      return_distributions=dist)
+    assert np.array_equal(got["counts"], want, equal_nan=True)
+    if dist:
+        assert np.array_equal(got["distributions"], want_d)
+    return got
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+@pytest.mark.parametrize("score_type", ["geometric_mean", "arithmetic_mean"])
+def test_liver_uploaded_labels_bit_exact(liver, mode, score_type):
+    """BASELINE.json configs[0] (bundled liver fixture, LRI_mouse, YOUNG vs OLD): counts and distributions."""
+    case = helpers.liver_case(liver, mode, score_type)
+    got = _check_uploaded(case["prob"], 200, seed=5, score_type=score_type, dist=True)
+    assert got["stats"]["kernel_launches"] > 0
+
+
+def test_liver_counts_do_not_depend_on_batch_size(liver_cases):
+    prob = liver_cases["cond"]["prob"]
+    pcond, pct = helpers.reference_like_labels(prob, 300, 9)
+    a = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, batch_size=128)["counts"]
+    b = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, batch_size=384)["counts"]
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+def test_group_means_bit_exact(liver_cases, mode):
+    """aggregate_cells on the original labels: means and detection rates (reference R/utils_cci.R:441-462, 262-266)."""
+    prob = liver_cases[mode]["prob"]
+    grp = np.asarray(prob.ct_code) + (prob.n_celltypes * np.asarray(prob.cond_code) if mode == "cond" else 0)
+    with Engine(prob) as eng:
+        means, dr = eng.group_means(detection_rate=True)
+    assert np.array_equal(means, oracle_c.group_means(prob, grp))
+    assert np.array_equal(dr, oracle_c.group_means(prob, grp, detection=True))
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+def test_device_philox_labels_match_cpu_restatement(liver_cases, mode):
+    prob = liver_cases[mode]["prob"]
+    with Engine(prob) as eng:
+        cond, ct = eng.draw_labels(200, seed=1234, perm_offset=1000)
+    cond_o, ct_o = oracle_c.philox_labels(prob, 200, seed=1234, perm_offset=1000)
+    assert np.array_equal(ct, ct_o)
+    if mode == "cond":
+        assert np.array_equal(cond, cond_o)
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+def test_device_generated_run_equals_oracle_on_the_same_labels(liver_cases, mode):
+    """Philox mode end to end: counts from on-device labels == oracle counts on the CPU restatement of those labels,
+    and sharding the replicate range (perm_offset) does not change the total."""
+    prob = liver_cases[mode]["prob"]
+    n, seed = 333, 77
+    cond_o, ct_o = oracle_c.philox_labels(prob, n, seed=seed)
+    want, _ = oracle_c.perm_counts(prob, ct_o, cond_o)
+    with Engine(prob) as eng:
+        whole = eng.run(n, seed=seed)["counts"]
+        a = eng.run(200, seed=seed, perm_offset=0)["counts"]
+        b = eng.run(n - 200, seed=seed, perm_offset=200)["counts"]
+    assert np.array_equal(whole, want, equal_nan=True)
+    assert np.array_equal(np.nan_to_num(a) + np.nan_to_num(b), np.nan_to_num(want))
+
+
+def test_uploaded_labels_that_are_not_stratified_shuffles_are_rejected(liver_cases):
+    prob = liver_cases["cond"]["prob"]
+    pcond, pct = helpers.reference_like_labels(prob, 4, 1)
+    pcond[2, :10] = 1 - pcond[2, :10]
+    with pytest.raises(_lib.ScdcError, match="do not preserve"):
+        perm_counts(prob, 4, perm_cond=pcond, perm_ct=pct)
+    pct[1, 0] = 200
+    with pytest.raises(_lib.ScdcError, match="outside"):
+        perm_counts(prob, 4, perm_cond=helpers.reference_like_labels(prob, 4, 1)[0], perm_ct=pct)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_cells=3000, n_genes=200, n_celltypes=6, n_conditions=2, n_lri=300, seed=1),     # K=12  -> J=4
+    dict(n_cells=4000, n_genes=150, n_celltypes=12, n_conditions=2, n_lri=250, seed=2),    # K=24  -> J=2
+    dict(n_cells=9000, n_genes=120, n_celltypes=30, n_conditions=2, n_lri=200, seed=3),    # K=60  -> J=1
+    dict(n_cells=2500, n_genes=180, n_celltypes=9, n_conditions=1, n_lri=300, seed=4),     # detection, K=9
+    dict(n_cells=20000, n_genes=60, n_celltypes=60, n_conditions=2, n_lri=100, seed=5, min_group=20),  # K=120
+])
+def test_synthetic_uploaded_labels_bit_exact(kw):
+    prob, ai, simple, mask = synthetic.make_problem(kw)
+    _check_uploaded(prob, 160, seed=kw["seed"], dist=(kw["seed"] == 1))
+
+
+def test_run_stat_analysis_mirror(liver_cases):
+    """The reference's own permutation tests (tests/testthat/test-everything.R:504-578): non-p-value columns unchanged,
+    p-value columns added with 1 outside the tested rows and NA for absent subunits, and p-values identical with and
+    without return_distributions under the same seed."""
+    case = liver_cases["cond"]
+    ai, simple = case["ai"], case["simple"]
+    a = run_stat_analysis(ai, simple, 10, False, "geometric_mean", False, seed=123)
+    b = run_stat_analysis(ai, simple, 10, True, "geometric_mean", False, seed=123)
+    for k, v in simple.items():
+        assert np.array_equal(a["cci_raw"][k], v, equal_nan=True)
+    for name in ("P_VALUE_DE", "P_VALUE_YOUNG", "P_VALUE_OLD", "L1_P_VALUE_DE", "L2_P_VALUE_DE", "R1_P_VALUE_DE",
+                 "R2_P_VALUE_DE", "R3_P_VALUE_DE"):
+        assert np.array_equal(a["cci_raw"][name], b["cci_raw"][name], equal_nan=True), name
+    p = a["cci_raw"]["P_VALUE_DE"]
+    assert np.all(p[~case["mask"]] == 1.0) and np.all((p >= 0) & (p <= 1))
+    assert np.isnan(a["cci_raw"]["L2_P_VALUE_DE"]).sum() > 0 and not np.isnan(a["cci_raw"]["L1_P_VALUE_DE"]).any()
+    d = b["distributions"]
+    assert set(d) == {"DISTRIBUTIONS_DE", "DISTRIBUTIONS_YOUNG", "DISTRIBUTIONS_OLD"}
+    assert d["DISTRIBUTIONS_DE"].shape == (8952, 11)
+    obs = d["DISTRIBUTIONS_DE"][:, -1]
+    pv = (np.abs(d["DISTRIBUTIONS_DE"][:, :10]) >= np.abs(obs)[:, None]).sum(1) / 10
+    assert np.array_equal(pv, a["cci_raw"]["P_VALUE_DE"][case["mask"]])
+    with pytest.raises(ValueError, match="1000"):
+        run_stat_analysis(ai, simple, 1500, True, "geometric_mean", False)
+
+
+def test_device_shuffles_are_uniform(liver_cases):
+    """Statistical parity with base::sample: every cell is equally likely to receive every label (chi-square on the
+    per-cell label frequencies over 4000 replicates)."""
+    prob = liver_cases["nocond"]["prob"]
+    n = 4000
+    with Engine(prob) as eng:
+        _, ct = eng.draw_labels(n, seed=99)
+    T, N = prob.n_celltypes, prob.n_cells
+    p = np.bincount(prob.ct_code, minlength=T) / N
+    obs = np.stack([(ct == t).sum(0) for t in range(T)], axis=1)        # [N, T]
+    chi2 = ((obs - n * p) ** 2 / (n * p)).sum()
+    dof = N * (T - 1)
+    assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
+    # adjacent cells are (nearly) uncorrelated: P(same label) = sum_t n_t (n_t - 1) / (N (N - 1))
+    nt = np.bincount(prob.ct_code, minlength=T)
+    expect = (nt * (nt - 1)).sum() / (N * (N - 1))
+    same = (ct[:, :-1] == ct[:, 1:]).mean()
+    assert abs(same - expect) < 5 * np.sqrt(expect * (1 - expect) / (n * (N - 1)))
