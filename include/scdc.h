@@ -100,7 +100,10 @@ typedef struct scdc_options {
   const uint8_t* perm_cond;
   const uint8_t* perm_ct;
   int32_t return_distributions; /* 1: also fill result.distributions (R/utils_permutation.R:304-426) */
-  int32_t reserved;
+  int32_t device_base;  /* scdc_perm_counts only: index (among the visible compute-capability-10.x devices) of the
+                           first device to use; 0 = default. One process per GPU sets it to its local rank. */
+  void* stream;         /* scdc_run only: NULL = the handle's own stream, else a cudaStream_t of the handle's device on
+                           which all work of the call is enqueued (lets a caller time it with its own CUDA events) */
 } scdc_options;
 
 typedef struct scdc_stats {
@@ -110,6 +113,7 @@ typedef struct scdc_stats {
   double ms_reduce;     /* device time, group-sum kernels (CUDA events) */
   double ms_score;      /* device time, score / compare / count kernels (CUDA events) */
   double ms_merge;      /* counter merge across GPUs + D2H */
+  double ms_device;     /* device time of the whole batch loop, first to last CUDA event (max over GPUs) */
   double reduce_bytes;  /* algorithmic bytes of all group-sum launches ("algorithmic bytes") */
   int64_t reduce_launches;
   int64_t kernel_launches; /* all kernels launched by the call */

@@ -42,14 +42,14 @@ class Options(C.Structure):
     _fields_ = [
         ("iterations", C.c_int64), ("seed", C.c_uint64), ("perm_offset", C.c_int64), ("score_type", C.c_int32),
         ("n_gpus", C.c_int32), ("precision", C.c_int32), ("batch_size", C.c_int32), ("perm_cond", C.c_void_p),
-        ("perm_ct", C.c_void_p), ("return_distributions", C.c_int32), ("reserved", C.c_int32),
+        ("perm_ct", C.c_void_p), ("return_distributions", C.c_int32), ("device_base", C.c_int32), ("stream", C.c_void_p),
     ]
 
 
 class Stats(C.Structure):
     _fields_ = [
         ("ms_total", C.c_double), ("ms_upload", C.c_double), ("ms_labels", C.c_double), ("ms_reduce", C.c_double),
-        ("ms_score", C.c_double), ("ms_merge", C.c_double), ("reduce_bytes", C.c_double),
+        ("ms_score", C.c_double), ("ms_merge", C.c_double), ("ms_device", C.c_double), ("reduce_bytes", C.c_double),
         ("reduce_launches", C.c_int64), ("kernel_launches", C.c_int64), ("batch_size", C.c_int64),
         ("n_gpus", C.c_int32), ("reserved", C.c_int32),
     ]

@@ -159,13 +159,14 @@ int validate_problem(const scdc_problem* p) {
       int g = p->sub_gene[(size_t)l * nS + s];
       if (g < -1 || g >= G) return fail(SCDC_EINVAL, "sub_gene[%d][%d] = %d out of range", l, s, g);
     }
-    if (p->sub_gene[(size_t)l * nS] < 0 || p->sub_gene[(size_t)l * nS + p->max_nL] < 0)
-      return fail(SCDC_EINVAL, "LRI %d lacks LIGAND_1 or RECEPTOR_1", l);
   }
   for (int r = 0; r < p->n_rows; ++r) {
     if (p->row_lri[r] < 0 || p->row_lri[r] >= p->n_lri || p->row_emit[r] < 0 || p->row_emit[r] >= T ||
         p->row_recv[r] < 0 || p->row_recv[r] >= T)
       return fail(SCDC_EINVAL, "row %d has an out-of-range LRI / emitter / receiver code", r);
+    const int l = p->row_lri[r];
+    if (p->sub_gene[(size_t)l * nS] < 0 || p->sub_gene[(size_t)l * nS + p->max_nL] < 0)
+      return fail(SCDC_EINVAL, "row %d: LRI %d lacks LIGAND_1 or RECEPTOR_1", r, l);
   }
   return SCDC_OK;
 }
@@ -382,9 +383,8 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
 
 // Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
 // h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
-int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st) {
+int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st, cudaStream_t s) {
   CU(cudaSetDevice(h->device));
-  cudaStream_t s = h->stream;
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K, R = h->R;
   const int B = pick_batch(h, o);
   const int Bw = B / 32;
@@ -495,6 +495,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
       st->ms_labels += a; st->ms_reduce += b; st->ms_score += c;
     }
+    if (evs.size() >= 2) {
+      float d = 0;
+      cudaEventElapsedTime(&d, evs.front(), evs.back());
+      st->ms_device += d;
+    }
     st->reduce_bytes += reduce_bytes;
     st->reduce_launches += reduce_launches;
     st->kernel_launches += launches;
@@ -552,14 +557,15 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
     return fail(SCDC_EINVAL, "return_distributions set but result.distributions is NULL");
   const double t0 = now_ms();
   memset(&res->stats, 0, sizeof res->stats);
-  rc = run_device(h, o, o->return_distributions ? res->distributions : nullptr, &res->stats);
+  cudaStream_t s = o->stream ? (cudaStream_t)o->stream : h->stream;
+  rc = run_device(h, o, o->return_distributions ? res->distributions : nullptr, &res->stats, s);
   if (rc) return rc;
   const double t1 = now_ms();
   const size_t n = (size_t)h->R * h->ncols;
   if (res->counts_device && n) {
-    scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->counts.p, (long long*)res->counts_device);
+    scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->counts.p, (long long*)res->counts_device);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(s));
     res->stats.kernel_launches += 1;
   }
   if (res->counts) {
@@ -588,8 +594,14 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   if (avail == 0)
     return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
   if (o->n_gpus < 0) return fail(SCDC_EINVAL, "n_gpus must be >= 0");
-  int W = (o->n_gpus == 0) ? avail : o->n_gpus;
-  if (W > avail) return fail(SCDC_ENOGPU, "n_gpus = %d but only %d compute-capability-10.x devices are visible", W, avail);
+  if (o->device_base < 0 || o->device_base >= avail)
+    return fail(SCDC_ENOGPU, "device_base = %d but %d compute-capability-10.x devices are visible", o->device_base, avail);
+  ids.erase(ids.begin(), ids.begin() + o->device_base);
+  const int usable = (int)ids.size();
+  int W = (o->n_gpus == 0) ? usable : o->n_gpus;
+  if (W > usable)
+    return fail(SCDC_ENOGPU, "n_gpus = %d but only %d compute-capability-10.x devices are visible from device_base %d", W,
+                usable, o->device_base);
   if (o->return_distributions) W = 1;  // <= 1000 replicates (R/utils_permutation.R:103-109): single GPU
   W = (int)std::min<int64_t>(W, std::max<int64_t>(1, o->iterations / 128));
   const double t0 = now_ms();
@@ -628,7 +640,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
         if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
         if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
         if (os[r].iterations > 0) {
-          rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r]);
+          rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
           if (rcs[r]) errs[r] = g_err;
         } else {
           cudaSetDevice(hs[r]->device);
@@ -684,6 +696,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     res->stats.ms_labels = std::max(res->stats.ms_labels, sts[r].ms_labels);
     res->stats.ms_reduce = std::max(res->stats.ms_reduce, sts[r].ms_reduce);
     res->stats.ms_score = std::max(res->stats.ms_score, sts[r].ms_score);
+    res->stats.ms_device = std::max(res->stats.ms_device, sts[r].ms_device);
     res->stats.ms_upload = std::max(res->stats.ms_upload, hs[r]->ms_upload);
     res->stats.reduce_bytes += sts[r].reduce_bytes;
     res->stats.reduce_launches += sts[r].reduce_launches;

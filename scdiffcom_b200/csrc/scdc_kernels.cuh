@@ -165,6 +165,8 @@ __global__ void k_pack_uploaded(int N, int T, int C, int nb, int Bpad, int J, co
   __syncthreads();
   int cell = cell0 + threadIdx.y, q = q0 + threadIdx.x;
   uint8_t vct = tile_ct[threadIdx.x][threadIdx.y], vcd = tile_cd[threadIdx.x][threadIdx.y];
+  if (vct >= T) vct = 0;  // out-of-range codes are reported by k_check_uploaded; keep the kernels in bounds meanwhile
+  if (vcd >= C) vcd = 0;
   uint32_t word = __ballot_sync(0xffffffffu, vcd == 1);
   if (cell < N) {
     if (C == 2 && threadIdx.x == 0) bits1[(size_t)cell * (Bpad / 32) + (q >> 5)] = word;
@@ -184,13 +186,13 @@ __global__ void k_check_uploaded(int N, int T, int C, const uint8_t* __restrict_
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     int c = (C == 2) ? up_cond[(size_t)q * N + i] : 0;
     int t2 = up_ct[(size_t)q * N + i];
-    if (c >= C || t2 >= T) { atomicExch(flag, 2); continue; }
+    if (c >= C || t2 >= T) { atomicMax(flag, 2); continue; }
     atomicAdd(&hist[c * T + ct[i]], 1);       // pass 1 groups: (cond', original cell type)
     atomicAdd(&hist[K + c * T + t2], 1);      // pass 2 groups: (cond', ct')
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * K; i += blockDim.x)
-    if ((uint32_t)hist[i] != expect[i % K]) atomicExch(flag, 1);
+    if ((uint32_t)hist[i] != expect[i % K]) atomicMax(flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

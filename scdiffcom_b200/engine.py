@@ -86,7 +86,7 @@ class PermutationProblem:
 
 
 def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-             n_cells, keep):
+             n_cells, keep, device_base=0, stream=None):
     o = Options()
     o.iterations = int(iterations)
     o.seed = int(seed) & (2**64 - 1)
@@ -103,6 +103,8 @@ def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm
             keep.append(a)
             setattr(o, name, _ptr(a))
     o.return_distributions = 1 if return_distributions else 0
+    o.device_base = int(device_base)
+    o.stream = C.c_void_p(int(stream)) if stream else None
     return o
 
 
@@ -121,14 +123,14 @@ def version() -> str:
 
 
 def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="geometric_mean", n_gpus=1, perm_offset=0,
-                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False):
+                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0):
     """One-shot `scdc_perm_counts` with HOST buffers (what the `.Call` wrapper does). Returns dict(counts [R_sub, ncols]
     float64 with NaN = NA, distributions or None, stats)."""
     lib = _lib.load()
     keep = []
     p = problem.c_struct()
     o = _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-                 problem.n_cells, keep)
+                 problem.n_cells, keep, device_base=device_base)
     counts = np.zeros((problem.n_rows, problem.ncols), dtype=np.uint64, order="F")
     res = Result()
     res.counts = _ptr(counts)
@@ -169,11 +171,11 @@ class Engine:
             pass
 
     def run(self, iterations, seed=42, score_type="geometric_mean", perm_offset=0, batch_size=0, perm_cond=None,
-            perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True):
+            perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True, stream=None):
         keep = []
         pr = self.problem
         o = _options(iterations, seed, score_type, perm_offset, 1, batch_size, perm_cond, perm_ct, return_distributions,
-                     pr.n_cells, keep)
+                     pr.n_cells, keep, stream=stream)
         res = Result()
         counts = None
         if want_host_counts:
