@@ -90,6 +90,10 @@ struct scdc_handle {
   DBuf<uint8_t> ct, cond;
   DBuf<uint32_t> urn_init, expect;
   std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
+  // K3 v2: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
+  DBuf<int> task_lri, task_beg, task_end, srow;
+  DBuf<double> thr;
+  int n_tasks = 0;
   // per-run workspace (grown on demand)
   DBuf<uint32_t> bits1, counts;
   DBuf<uint8_t> lab2, up_cond, up_ct;
@@ -184,6 +188,19 @@ int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* 
     return fail(SCDC_EINVAL, "differential validation mode needs both perm_cond and perm_ct");
   return SCDC_OK;
 }
+
+// smallest y with sqrt_rn(y) >= o: (sqrt(x) >= o) == (x >= y) for every x, because sqrt_rn is monotone non-decreasing
+double product_threshold(double o) {
+  if (std::isnan(o)) return o;
+  if (o <= 0.0) return 0.0;  // sqrt(x) >= o for every x >= 0; x < 0 gives NaN on both sides (false)
+  if (std::isinf(o)) return o;
+  double y = o * o;
+  while (y > 0.0 && std::sqrt(std::nextafter(y, -INFINITY)) >= o) y = std::nextafter(y, -INFINITY);
+  while (std::sqrt(y) < o) y = std::nextafter(y, INFINITY);
+  return y;
+}
+
+constexpr int kScoreThreads = 256, kScoreRPT = 2;
 
 // Fenwick tree (1-based) over counts n[0..T)
 void fenwick_build(const uint32_t* n, int T, uint32_t* tree /*[T], tree[i-1] = node i*/) {
@@ -310,6 +327,31 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
       CU(h->rowidx_s.upload(rows_s.data(), h->nnz, s));
       CU(h->values_s.upload(vals_s.data(), h->nnz, s));
     }
+    // K3 v2 work list: rows stably sorted by LRI, each LRI cut into slices of kScoreThreads * kScoreRPT rows
+    std::vector<int> srow(h->R), t_lri, t_beg, t_end;
+    for (int r = 0; r < h->R; ++r) srow[r] = r;
+    std::stable_sort(srow.begin(), srow.end(), [&](int a, int b) { return p->row_lri[a] < p->row_lri[b]; });
+    const int rpb = kScoreThreads * kScoreRPT;
+    for (int b = 0; b < h->R;) {
+      int e = b;
+      while (e < h->R && p->row_lri[srow[e]] == p->row_lri[srow[b]]) ++e;
+      for (int c = b; c < e; c += rpb) {
+        t_lri.push_back(p->row_lri[srow[b]]);
+        t_beg.push_back(c);
+        t_end.push_back(std::min(e, c + rpb));
+      }
+      b = e;
+    }
+    h->n_tasks = (int)t_lri.size();
+    std::vector<double> thr((size_t)h->R * C);
+    for (int c = 0; c < C; ++c)
+      for (int r = 0; r < h->R; ++r)
+        thr[(size_t)c * h->R + r] = product_threshold(p->observed[(size_t)(C == 2 ? 1 + c : 0) * h->R + r]);
+    CU(h->srow.upload(srow.data(), srow.size(), s));
+    CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
+    CU(h->task_beg.upload(t_beg.data(), t_beg.size(), s));
+    CU(h->task_end.upload(t_end.data(), t_end.size(), s));
+    CU(h->thr.upload(thr.data(), thr.size(), s));
     CU(h->flag.alloc(1));
     CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
   } catch (const std::bad_alloc&) {
@@ -459,7 +501,31 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     reduce_bytes += (double)C * ((double)h->nnz * (sv + 4.0) + 4.0 * (G + 1)) + (double)B * N * (C == 2 ? 1.125 : 1.0) +
                     (double)C * B * K * G * sv;
     CU(mark());
-    if (R > 0) {
+    if (R > 0 && !dist_host && !env_int("SCDC_SCORE_V1", 0)) {
+      scdc::ScoreV2Args A;
+      A.G = G; A.T = T; A.Tp = T | 1; A.K = K; A.nL = h->nL; A.nS = h->nS; A.ncols = h->ncols; A.score_type = o->score_type;
+      A.nChunks = (nb + 31) / 32; A.n_valid = nb; A.R = R;
+      const int n_arr = (C == 2) ? 8 + h->nS : 2;
+      int P = 32;
+      while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > 100 * 1024) P >>= 1;
+      P = env_int("SCDC_SCORE_P", P);
+      A.P = P;
+      const size_t smem = (size_t)n_arr * P * A.Tp * 8;
+      A.task_lri = h->task_lri.p; A.task_beg = h->task_beg.p; A.task_end = h->task_end.p; A.srow = h->srow.p;
+      A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p; A.thr = h->thr.p;
+      A.M1 = h->M1.p; A.M2 = h->M2.p; A.counts = h->counts.p;
+      if (C == 2) {
+        auto kern = scdc::k_score_v2<2, kScoreRPT>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<h->n_tasks, kScoreThreads, smem, s>>>(A);
+      } else {
+        auto kern = scdc::k_score_v2<1, kScoreRPT>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<h->n_tasks, kScoreThreads, smem, s>>>(A);
+      }
+      CU(cudaGetLastError());
+      ++launches;
+    } else if (R > 0) {
       scdc::ScoreArgs A;
       A.R = R; A.G = G; A.T = T; A.C = C; A.nL = h->nL; A.nR = h->nR; A.ncols = h->ncols; A.score_type = o->score_type;
       A.nChunks = (nb + 31) / 32; A.n_valid = nb;

@@ -445,6 +445,167 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K3 (v2, the production path): factorised per LRI. A block owns one LRI and a slice of its tested rows (thread = row,
+// RPT rows per thread, counters and observed values in registers for the whole launch) and walks the batch P replicates
+// at a time:
+//   stage A: min over the LRI's present ligand subunits per (condition, cell type) and the same for the receptor side
+//            (pmin(na.rm = TRUE), reference R/utils_cci.R:613-653), plus the per-subunit cond2 - cond1 differences, go to
+//            shared memory as [replicate][cell type] tiles (2T * P coalesced reads of the group means per pass);
+//   stage B: every row combines its emitter / receiver entries: score, DE difference, `>=` compares, register counters.
+// No ballots, no atomics, no re-reading of the means per row. The one-sided geometric columns compare the PRODUCT with a
+// host-precomputed threshold thr = min{y : sqrt_rn(y) >= observed}; sqrt_rn is monotone, so
+// (sqrt(a*b) >= observed) == (a*b >= thr) exactly and the fp64 sqrt disappears from those columns.
+// ------------------------------------------------------------------------------------------------------------------
+struct ScoreV2Args {
+  int G, T, Tp, K, nL, nS, ncols, score_type;
+  int nChunks, n_valid, P;
+  int R;
+  const int* task_lri;
+  const int* task_beg;
+  const int* task_end;
+  const int* srow;      // [R] original row id of each LRI-sorted position
+  const int* sub_gene;
+  const int* row_emit;
+  const int* row_recv;
+  const double* obs;    // column-major [R][ncols], original row ids
+  const double* thr;    // column-major [R][C] product thresholds (geometric one-sided columns), original row ids
+  const double* M1;
+  const double* M2;
+  uint32_t* counts;
+};
+
+template <int C, int RPT>
+__global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
+  extern __shared__ __align__(16) double sm_d[];
+  __shared__ int s_gs[8];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
+  const int T = A.T, Tp = A.Tp, P = A.P, K = A.K, nL = A.nL, nS = A.nS;
+  if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
+  constexpr int NOB = (C == 2) ? 11 : 1;
+  int e_[RPT], r_[RPT], rid[RPT];
+  double ob[RPT][NOB], th[RPT][2];
+  uint32_t cnt[RPT][NOB];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int pos = rb + tid + q * nthr;
+    rid[q] = (pos < re) ? A.srow[pos] : -1;
+    e_[q] = r_[q] = 0;
+#pragma unroll
+    for (int c = 0; c < NOB; ++c) { ob[q][c] = 0.0; cnt[q][c] = 0; }
+    th[q][0] = th[q][1] = 0.0;
+    if (rid[q] >= 0) {
+      e_[q] = A.row_emit[rid[q]];
+      r_[q] = A.row_recv[rid[q]];
+#pragma unroll
+      for (int c = 0; c < NOB; ++c)
+        if (c < A.ncols) ob[q][c] = A.obs[(size_t)c * A.R + rid[q]];
+      th[q][0] = A.thr[rid[q]];
+      if (C == 2) th[q][1] = A.thr[(size_t)A.R + rid[q]];
+    }
+  }
+  const int tile = P * Tp;  // doubles per staged array
+  const int nHalf = 32 / P;
+  for (int ch = 0; ch < A.nChunks; ++ch) {
+    for (int hf = 0; hf < nHalf; ++hf) {
+      const int pbase = ch * 32 + hf * P;
+      if (pbase >= A.n_valid) break;
+      __syncthreads();
+      // ---------------- stage A ----------------
+      for (int item = tid; item < 2 * T * P; item += nthr) {
+        const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+        const int s0 = side ? nL : 0, s1 = side ? nS : nL;
+        const size_t lane_off = (size_t)hf * P + p;
+        if (C == 1) {
+          double m = 0.0;
+          bool h = false;
+          for (int s = s0; s < s1; ++s) {
+            const int g = s_gs[s];
+            if (g >= 0) {
+              double v = A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane_off];
+              m = h ? fmin(m, v) : v;
+              h = true;
+            }
+          }
+          sm_d[side * tile + p * Tp + ct] = m;
+        } else {
+          double m10 = 0.0, m11 = 0.0, m20 = 0.0, m21 = 0.0;
+          bool h = false;
+          for (int s = s0; s < s1; ++s) {
+            const int g = s_gs[s];
+            double d = 0.0;
+            if (g >= 0) {
+              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane_off, i1 = i0 + (size_t)T * 32;
+              const double v10 = A.M1[i0], v11 = A.M1[i1], v20 = A.M2[i0], v21 = A.M2[i1];
+              d = v11 - v10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
+              m10 = h ? fmin(m10, v10) : v10; m11 = h ? fmin(m11, v11) : v11;
+              m20 = h ? fmin(m20, v20) : v20; m21 = h ? fmin(m21, v21) : v21;
+              h = true;
+            }
+            sm_d[(8 + s) * tile + p * Tp + ct] = d;
+          }
+          double* base = sm_d + side * 2 * tile + p * Tp + ct;  // arrays: pass*4 + side*2 + cond
+          base[0] = m10; base[tile] = m11; base[4 * tile] = m20; base[5 * tile] = m21;
+        }
+      }
+      __syncthreads();
+      // ---------------- stage B ----------------
+      const int pmax = min(P, A.n_valid - pbase);
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (rid[q] < 0) continue;
+        const int e = e_[q], r = r_[q];
+        if (C == 1) {
+          const double* pa = sm_d + e;
+          const double* pb = sm_d + tile + r;
+          if (A.score_type == 0) {
+#pragma unroll 4
+            for (int p = 0; p < pmax; ++p) cnt[q][0] += (pa[p * Tp] * pb[p * Tp] >= th[q][0]) ? 1u : 0u;
+          } else {
+#pragma unroll 4
+            for (int p = 0; p < pmax; ++p) cnt[q][0] += ((pa[p * Tp] + pb[p * Tp]) / 2 >= ob[q][0]) ? 1u : 0u;
+          }
+        } else {
+          const double aob0 = fabs(ob[q][0]);
+#pragma unroll 2
+          for (int p = 0; p < pmax; ++p) {
+            const double* pa = sm_d + p * Tp + e;            // ligand side arrays 0,1 (pass 1), 4,5 (pass 2)
+            const double* pb = sm_d + 2 * tile + p * Tp + r;  // receptor side arrays 2,3 (pass 1), 6,7 (pass 2)
+            const double a10 = pa[0], a11 = pa[tile], a20 = pa[4 * tile], a21 = pa[5 * tile];
+            const double b10 = pb[0], b11 = pb[tile], b20 = pb[4 * tile], b21 = pb[5 * tile];
+            double de;
+            if (A.score_type == 0) {
+              de = sqrt(a11 * b11) - sqrt(a10 * b10);
+              cnt[q][1] += (a20 * b20 >= th[q][0]) ? 1u : 0u;
+              cnt[q][2] += (a21 * b21 >= th[q][1]) ? 1u : 0u;
+            } else {
+              de = (a11 + b11) / 2 - (a10 + b10) / 2;
+              cnt[q][1] += ((a20 + b20) / 2 >= ob[q][1]) ? 1u : 0u;
+              cnt[q][2] += ((a21 + b21) / 2 >= ob[q][2]) ? 1u : 0u;
+            }
+            cnt[q][0] += (fabs(de) >= aob0) ? 1u : 0u;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              if (s < nS) {
+                const double d = sm_d[(8 + s) * tile + p * Tp + (s < nL ? e : r)];
+                cnt[q][3 + s] += (fabs(d) >= fabs(ob[q][3 + s])) ? 1u : 0u;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rid[q] < 0) continue;
+#pragma unroll
+    for (int c = 0; c < NOB; ++c)
+      if (c < A.ncols) A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Observed-pass helper (aggregate_cells on the original labels): one thread per gene, sequential over the column.
 // out is column-major [K][G]: out[g*K + k]. mode 0: sum of x ; mode 1: sum of 1*(x > 0).
 // ------------------------------------------------------------------------------------------------------------------
