@@ -160,41 +160,31 @@ int oracle_group_means(int N, int G, int K, const int32_t* colptr, const int32_t
   return 0;
 }
 
-/* ---- restatement of the device label generator (Philox4x32-10 + sequential urn draws) ------------------------------ */
-typedef struct {
-  uint32_t c0, c1, c2, c3, k0, k1, out[4];
-  int have;
-} philox_t;
-
-static void philox_refill(philox_t* s) {
-  uint32_t x0 = s->c0, x1 = s->c1, x2 = s->c2, x3 = s->c3, a = s->k0, b = s->k1;
+/* ---- restatement of the device label generator (scdc_kernels.cuh: k_draw_labels) ----------------------------------
+ * Philox4x32-10, counter (visit, block, replicate lo, replicate hi), key = seed. Draw d (0 = condition, 1 = cell type) of
+ * visit i, attempt a = word 2a + d of the visit's stream. Cells are visited in cell order (detection) or stably sorted by
+ * cell type (differential). Sequential urn draws: next label k with probability remaining[k] / remaining total. */
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
   for (int r = 0; r < 10; ++r) {
-    uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
-    uint32_t y0 = (uint32_t)(p1 >> 32) ^ x1 ^ a, y1 = (uint32_t)p1, y2 = (uint32_t)(p0 >> 32) ^ x3 ^ b, y3 = (uint32_t)p0;
-    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-    a += 0x9E3779B9u; b += 0xBB67AE85u;
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t y0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, y1 = (uint32_t)p1, y2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, y3 = (uint32_t)p0;
+    c0 = y0; c1 = y1; c2 = y2; c3 = y3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  s->out[0] = x0; s->out[1] = x1; s->out[2] = x2; s->out[3] = x3;
-  s->have = 4;
-  if (++s->c0 == 0) ++s->c1;
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-static uint32_t philox_next(philox_t* s) {
-  if (s->have == 0) philox_refill(s);
-  uint32_t v = s->out[4 - s->have];
-  --s->have;
-  return v;
+static uint32_t stream_word(uint32_t visit, int w, uint64_t rep, uint64_t seed) {
+  uint32_t o[4];
+  philox4x32_10(visit, (uint32_t)(w >> 2), (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  return o[w & 3];
 }
-static uint32_t philox_bounded(philox_t* s, uint32_t range) {
-  uint64_t m = (uint64_t)philox_next(s) * range;
-  uint32_t l = (uint32_t)m;
-  if (l < range) {
-    uint32_t t = (0u - range) % range;
-    while (l < t) {
-      m = (uint64_t)philox_next(s) * range;
-      l = (uint32_t)m;
-    }
+/* Lemire's unbiased bounded integer: attempts a = 0, 1, .. until accepted */
+static uint32_t bounded_draw(uint32_t visit, int d, uint32_t range, uint64_t rep, uint64_t seed) {
+  const uint32_t t = (0u - range) % range;
+  for (int a = 0;; ++a) {
+    uint64_t m = (uint64_t)stream_word(visit, 2 * a + d, rep, seed) * range;
+    if ((uint32_t)m >= t) return (uint32_t)(m >> 32);
   }
-  return (uint32_t)(m >> 32);
 }
 /* smallest k with n[0] + .. + n[k] > u */
 static int urn_pick(uint32_t* n, int T, uint32_t u) {
@@ -211,30 +201,39 @@ int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int3
   uint32_t* base = (uint32_t*)calloc((size_t)2 * T, sizeof(uint32_t));
   uint32_t* remc = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)2 * T);
   uint32_t* urn = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)2 * T);
-  if (!base || !remc || !urn) return 1;
+  int32_t* visit = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+  if (!base || !remc || !urn || !visit) return 1;
   for (int i = 0; i < N; ++i) ++base[(size_t)((C == 2) ? cond_code[i] : 0) * T + ct_code[i]];
+  if (C == 2) { /* stable sort of the cells by cell type */
+    int v = 0;
+    for (int t = 0; t < T; ++t)
+      for (int i = 0; i < N; ++i)
+        if (ct_code[i] == t) visit[v++] = i;
+  } else {
+    for (int i = 0; i < N; ++i) visit[i] = i;
+  }
   for (int64_t q = 0; q < n; ++q) {
-    philox_t s = {0, 0, (uint32_t)(uint64_t)(perm_offset + q), (uint32_t)((uint64_t)(perm_offset + q) >> 32),
-                  (uint32_t)seed, (uint32_t)(seed >> 32), {0, 0, 0, 0}, 0};
+    const uint64_t rep = (uint64_t)(perm_offset + q);
     memcpy(remc, base, sizeof(uint32_t) * (size_t)2 * T);
     memcpy(urn, base, sizeof(uint32_t) * (size_t)2 * T);
     uint32_t tot[2] = {0, 0};
     for (int t = 0; t < T; ++t) { tot[0] += base[t]; tot[1] += base[(size_t)T + t]; }
-    for (int i = 0; i < N; ++i) {
+    for (int v = 0; v < N; ++v) {
+      const int i = visit[v];
       int c = 0;
       if (C == 2) {
-        int t = ct_code[i];
-        uint32_t r0 = remc[t], r1 = remc[(size_t)T + t];
-        uint32_t u = philox_bounded(&s, r0 + r1);
+        const int t = ct_code[i];
+        const uint32_t r0 = remc[t], r1 = remc[(size_t)T + t];
+        const uint32_t u = bounded_draw((uint32_t)v, 0, r0 + r1, rep, seed);
         c = (u < r0) ? 0 : 1;
         --remc[(size_t)c * T + t];
         cond_out[(size_t)q * N + i] = (uint8_t)c;
       }
-      uint32_t u = philox_bounded(&s, tot[c]);
+      const uint32_t u = bounded_draw((uint32_t)v, 1, tot[c], rep, seed);
       --tot[c];
       ct_out[(size_t)q * N + i] = (uint8_t)urn_pick(urn + (size_t)c * T, T, u);
     }
   }
-  free(base); free(remc); free(urn);
+  free(base); free(remc); free(urn); free(visit);
   return 0;
 }

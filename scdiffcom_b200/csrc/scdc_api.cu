@@ -81,22 +81,23 @@ struct scdc_handle {
   int device = 0;
   int N = 0, G = 0, T = 0, C = 0, L = 0, R = 0, nL = 0, nR = 0, K = 0, ncols = 0, nS = 0;
   size_t nnz = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream_labels = nullptr;
   int num_sms = 148;
   size_t smem_optin = 0;
   // problem
   DBuf<int> colptr, rowidx, segptr, rowidx_s, gene_order, sub_gene, row_lri, row_emit, row_recv;
   DBuf<double> values, values_s, ngroup, obs;
   DBuf<uint8_t> ct, cond;
-  DBuf<uint32_t> urn_init, expect;
+  DBuf<uint32_t> expect;      // n(cell type, condition) as uint32 [K]
+  DBuf<int> visit, ct_seg;     // K1 visit order (differential: cells stably sorted by cell type) and its segments
   std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
   // K3 v2: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
   DBuf<double> thr;
   int n_tasks = 0;
   // per-run workspace (grown on demand)
-  DBuf<uint32_t> bits1, counts;
-  DBuf<uint8_t> lab2, up_cond, up_ct;
+  DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
+  DBuf<uint8_t> lab2[2], up_cond, up_ct;
   DBuf<double> M1, M2, dist;
   DBuf<int> flag;
   double ms_upload = 0;
@@ -202,15 +203,6 @@ double product_threshold(double o) {
 
 constexpr int kScoreThreads = 256, kScoreRPT = 2;
 
-// Fenwick tree (1-based) over counts n[0..T)
-void fenwick_build(const uint32_t* n, int T, uint32_t* tree /*[T], tree[i-1] = node i*/) {
-  for (int i = 1; i <= T; ++i) {
-    uint32_t s = 0;
-    for (int j = i - (i & -i) + 1; j <= i; ++j) s += n[j - 1];
-    tree[i - 1] = s;
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -223,6 +215,7 @@ void scdc_release(scdc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream_labels) cudaStreamDestroy(h->stream_labels);
   delete h;
 }
 
@@ -247,6 +240,11 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
   h->ncols = (h->C == 2) ? 3 + h->nS : 1;
   h->nnz = (size_t)p->colptr[h->G];
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {  // label generation runs one batch ahead with few, long-lived warps: give its blocks scheduling priority
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&h->stream_labels, cudaStreamNonBlocking, hi));
+  }
   int v = 0;
   CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
   h->num_sms = v;
@@ -270,20 +268,17 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       return (p->colptr[a + 1] - p->colptr[a]) > (p->colptr[b + 1] - p->colptr[b]);
     });
-    // urn initial state for K1
-    std::vector<uint32_t> init;
+    // K1 visit order: differential mode walks the cells grouped by cell type (stable), detection mode in cell order
+    std::vector<int> visit, ct_seg;
     if (C == 2) {
-      init.resize((size_t)4 * T + 2);
-      for (int t = 0; t < T; ++t) { init[t] = ng[t]; init[T + t] = ng[(size_t)T + t]; }
-      fenwick_build(&ng[0], T, &init[(size_t)2 * T]);
-      fenwick_build(&ng[(size_t)T], T, &init[(size_t)3 * T]);
-      uint32_t n0 = 0, n1 = 0;
-      for (int t = 0; t < T; ++t) { n0 += ng[t]; n1 += ng[(size_t)T + t]; }
-      init[(size_t)4 * T] = n0; init[(size_t)4 * T + 1] = n1;
-    } else {
-      init.resize((size_t)T + 2);
-      fenwick_build(&ng[0], T, &init[0]);
-      init[T] = (uint32_t)N; init[(size_t)T + 1] = 0;
+      visit.resize(N);
+      ct_seg.assign((size_t)T + 1, 0);
+      for (int i = 0; i < N; ++i) ++ct_seg[(size_t)ct8[i] + 1];
+      for (int t = 0; t < T; ++t) ct_seg[(size_t)t + 1] += ct_seg[t];
+      std::vector<int> cur(ct_seg.begin(), ct_seg.end() - 1);
+      for (int i = 0; i < N; ++i) visit[cur[ct8[i]]++] = i;
+      CU(h->visit.upload(visit.data(), visit.size(), s));
+      CU(h->ct_seg.upload(ct_seg.data(), ct_seg.size(), s));
     }
     CU(h->colptr.upload(p->colptr, (size_t)G + 1, s));
     CU(h->rowidx.upload(p->rowidx, h->nnz, s));
@@ -293,7 +288,6 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
     CU(h->ngroup.upload(ngd.data(), K, s));
     CU(h->expect.upload(ng.data(), K, s));
     CU(h->gene_order.upload(order.data(), G, s));
-    CU(h->urn_init.upload(init.data(), init.size(), s));
     CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
     CU(h->row_lri.upload(p->row_lri, h->R, s));
     CU(h->row_emit.upload(p->row_emit, h->R, s));
@@ -366,6 +360,30 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
 
 namespace {
 
+template <int NG>
+cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int J, uint32_t* bits1,
+                           uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
+  auto kern = scdc::k_draw_labels<NG>;
+  const size_t smem = (size_t)h->C * NG * 8 * 32 * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<B / 32, 32, smem, s>>>(h->N, h->T, h->C, h->C == 2 ? h->visit.p : nullptr, h->ct_seg.p, h->expect.p, seed, perm0, B, J,
+                               bits1, lab2, dbg_cond, dbg_ct);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_draw(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int J, uint32_t* bits1,
+                        uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
+  const int T = h->T;
+  if (T <= 16) return launch_draw_ng<2>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 32) return launch_draw_ng<4>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 64) return launch_draw_ng<8>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 128) return launch_draw_ng<16>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+  return launch_draw_ng<32>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+}
+
 struct ScatterPlan {
   int J, W, blocks_per_sm;
   size_t smem;
@@ -397,13 +415,14 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
 }
 
 template <int J>
-cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, cudaStream_t s) {
+cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
+                           cudaStream_t s) {
   auto kern = scdc::k_scatter<J>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
   dim3 grid(h->G, (nCJ + pl.W - 1) / pl.W);
-  kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, h->lab2.p, Bpad,
+  kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
                                         h->ngroup.p, h->gene_order.p, h->M2.p);
   return cudaGetLastError();
 }
@@ -432,10 +451,33 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   const int Bw = B / 32;
   const ScatterPlan pl = plan_scatter(h, B);
   const bool uploaded = o->perm_ct != nullptr;
+  // Device-drawn labels: K1 is one thread per replicate and sequential over the cells, so its run time hardly depends on
+  // how many replicates it draws. It therefore draws a whole SUPER-batch (SB replicates, as many as the label memory cap
+  // allows — normally all of them) in one launch; the reduction then walks it in batches of B. With several
+  // super-batches the label buffers are double-buffered and K1 runs one super-batch ahead on a second stream.
+  const int64_t iters_pad = ((o->iterations + B - 1) / B) * B;
+  int64_t SB = B;
+  if (!uploaded) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double per_rep = (double)N * (C == 2 ? 1.125 : 1.0);
+    const double cap = std::min((double)free_b * 0.2, 8.0e9);
+    SB = std::max<int64_t>(B, ((int64_t)(cap / per_rep) / B) * B);
+    SB = std::min<int64_t>(SB, iters_pad);
+    const int sb_env = env_int("SCDC_SUPER_BATCH", 0);
+    if (sb_env > 0) SB = std::min<int64_t>(iters_pad, std::max<int64_t>(B, ((int64_t)sb_env / B) * B));
+  }
+  const int SBw = (int)(SB / 32);
+  const bool pipelined = !uploaded && SB < iters_pad;
+  const int nbuf = pipelined ? 2 : 1;
+  cudaStream_t sL = pipelined ? h->stream_labels : s;
   const int ncols_d = (C == 2) ? 3 : 1;
   const size_t msz = (size_t)Bw * G * K * 32;
-  CU(h->lab2.ensure((size_t)N * B));
-  if (C == 2) { CU(h->bits1.ensure((size_t)N * Bw)); CU(h->M1.ensure(msz)); }
+  for (int i = 0; i < nbuf; ++i) {
+    CU(h->lab2[i].ensure((size_t)N * SB));
+    if (C == 2) CU(h->bits1[i].ensure((size_t)N * SBw));
+  }
+  if (C == 2) CU(h->M1.ensure(msz));
   CU(h->M2.ensure(msz));
   CU(h->counts.ensure((size_t)R * h->ncols + 1));
   CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
@@ -445,29 +487,62 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
   }
   if (dist_host) CU(h->dist.ensure((size_t)B * ncols_d * R));
-  const int draw_threads = 32;
-  const size_t draw_smem = (size_t)((C == 2) ? 4 * T : T) * draw_threads * sizeof(uint32_t);
-  if (!uploaded && draw_smem > 48 * 1024)
-    CU(cudaFuncSetAttribute(scdc::k_draw_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)draw_smem));
-  std::vector<cudaEvent_t> evs;
-  auto mark = [&]() -> cudaError_t {
+  std::vector<cudaEvent_t> evs, evl;  // timing events on the compute stream (3 per batch) / label stream (2 per batch)
+  auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st_) -> cudaError_t {
     cudaEvent_t e;
     cudaError_t rc = cudaEventCreate(&e);
     if (rc != cudaSuccess) return rc;
-    evs.push_back(e);
-    return cudaEventRecord(e, s);
+    v.push_back(e);
+    return cudaEventRecord(e, st_);
   };
   struct EvGuard {
     std::vector<cudaEvent_t>& v;
     ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
-  } guard{evs};
+  } guard{evs}, guard2{evl};
+  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  struct SyncGuard {
+    cudaEvent_t* a; cudaEvent_t* b;
+    ~SyncGuard() { for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } }
+  } guard3{ready, freed};
+  bool freed_set[2] = {false, false};
+  if (pipelined) {
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+    }
+  }
   int64_t launches = 0, reduce_launches = 0;
   double reduce_bytes = 0;
   const double sv = 8.0;
+  cudaEvent_t ev_begin = nullptr;
+  CU(mark(evs, s));  // evs[0]: start of the whole loop on the compute stream
+  ev_begin = evs[0];
+  (void)ev_begin;
+  auto issue_labels = [&](int64_t sb_start, int buf) -> int {
+    if (pipelined && freed_set[buf]) CU(cudaStreamWaitEvent(sL, freed[buf], 0));
+    CU(mark(evl, sL));
+    CU(launch_draw(h, sL, o->seed, o->perm_offset + sb_start, (int)SB, pl.J, h->bits1[buf].p, h->lab2[buf].p, nullptr, nullptr));
+    CU(mark(evl, sL));
+    if (pipelined) CU(cudaEventRecord(ready[buf], sL));
+    ++launches;
+    return SCDC_OK;
+  };
+  if (pipelined) {
+    // the label stream must not run ahead of work already queued on the compute stream (e.g. a previous run's readers)
+    cudaEvent_t start;
+    CU(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    cudaError_t e1 = cudaEventRecord(start, s), e2 = cudaStreamWaitEvent(sL, start, 0);
+    cudaEventDestroy(start);
+    CU(e1); CU(e2);
+    int rc = issue_labels(0, 0);
+    if (rc) return rc;
+  }
   for (int64_t done = 0; done < o->iterations; done += B) {
     const int nb = (int)std::min<int64_t>(B, o->iterations - done);
-    CU(mark());
+    const int64_t sb_idx = done / SB, in_sb = done % SB;  // position inside the current super-batch
+    const int buf = pipelined ? (int)(sb_idx & 1) : 0;
     if (uploaded) {
+      CU(mark(evl, s));
       CU(cudaMemcpyAsync(h->up_ct.p, o->perm_ct + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
       if (C == 2)
         CU(cudaMemcpyAsync(h->up_cond.p, o->perm_cond + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
@@ -475,32 +550,44 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
                                                                   h->flag.p);
       dim3 grid((N + 31) / 32, B / 32), block(32, 32);
       scdc::k_pack_uploaded<<<grid, block, 0, s>>>(N, T, C, nb, B, pl.J, h->ct.p, h->cond.p, h->up_cond.p, h->up_ct.p,
-                                                   h->bits1.p, h->lab2.p);
+                                                   h->bits1[0].p, h->lab2[0].p);
+      CU(cudaGetLastError());
+      CU(mark(evl, s));
       launches += 2;
-    } else {
-      scdc::k_draw_labels<<<B / draw_threads, draw_threads, draw_smem, s>>>(
-          N, T, C, h->ct.p, h->urn_init.p, o->seed, o->perm_offset + done, B, pl.J, h->bits1.p, h->lab2.p, nullptr, nullptr);
-      launches += 1;
+    } else if (in_sb == 0) {
+      if (!pipelined) {
+        int rc = issue_labels(done, 0);
+        if (rc) return rc;
+      } else {
+        if (done + SB < o->iterations) {  // next super-batch's labels, enqueued first so that they overlap this one's compute
+          int rc = issue_labels(done + SB, buf ^ 1);
+          if (rc) return rc;
+        }
+        CU(cudaStreamWaitEvent(s, ready[buf], 0));
+      }
     }
-    CU(cudaGetLastError());
-    CU(mark());
+    const uint8_t* lab2_b = h->lab2[buf].p + in_sb;            // row stride SB bytes
+    const uint32_t* bits1_b = (C == 2) ? h->bits1[buf].p + in_sb / 32 : nullptr;  // row stride SBw words
+    CU(mark(evs, s));
     if (C == 2) {
       const int nWC = B / 128, W = 8;
       const long long tasks = (long long)G * nWC;
       scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, T, nWC, h->segptr.p, h->rowidx_s.p,
-                                                                           h->values_s.p, h->bits1.p, Bw, h->ngroup.p,
+                                                                           h->values_s.p, bits1_b, SBw, h->ngroup.p,
                                                                            h->gene_order.p, h->M1.p);
       CU(cudaGetLastError());
       ++launches; ++reduce_launches;
     }
-    cudaError_t le = (pl.J == 4) ? launch_scatter<4>(h, pl, B, s) : (pl.J == 2) ? launch_scatter<2>(h, pl, B, s)
-                                                                                : launch_scatter<1>(h, pl, B, s);
+    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, (int)SB, s)
+                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, (int)SB, s)
+                                   : launch_scatter<1>(h, pl, B, lab2_b, (int)SB, s);
     CU(le);
     ++launches; ++reduce_launches;
+    if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz * (sv + 4.0) + 4.0 * (G + 1)) + (double)B * N * (C == 2 ? 1.125 : 1.0) +
                     (double)C * B * K * G * sv;
-    CU(mark());
+    CU(mark(evs, s));
     if (R > 0 && !dist_host && !env_int("SCDC_SCORE_V1", 0)) {
       scdc::ScoreV2Args A;
       A.G = G; A.T = T; A.Tp = T | 1; A.K = K; A.nL = h->nL; A.nS = h->nS; A.ncols = h->ncols; A.score_type = o->score_type;
@@ -540,10 +627,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
         CU(cudaMemcpyAsync(dist_host + (size_t)done * ncols_d * R, h->dist.p, (size_t)nb * ncols_d * R * sizeof(double),
                            cudaMemcpyDeviceToHost, s));
     }
-    CU(mark());
+    CU(mark(evs, s));
     if (uploaded || dist_host) CU(cudaStreamSynchronize(s));  // host source / destination buffers are reused per batch
   }
   CU(cudaStreamSynchronize(s));
+  if (pipelined) CU(cudaStreamSynchronize(sL));
   if (uploaded) {
     int flag = 0;
     CU(cudaMemcpy(&flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -554,12 +642,16 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
                   "run_stat_iteration shuffle (reference R/utils_permutation.R:536-569)");
   }
   if (st) {
-    for (size_t i = 0; i + 3 < evs.size(); i += 4) {
-      float a = 0, b = 0, c = 0;
-      cudaEventElapsedTime(&a, evs[i], evs[i + 1]);
-      cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]);
-      cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
-      st->ms_labels += a; st->ms_reduce += b; st->ms_score += c;
+    for (size_t i = 1; i + 2 < evs.size(); i += 3) {  // evs[0] = loop start; then per batch: ready, reduced, scored
+      float b = 0, c = 0;
+      cudaEventElapsedTime(&b, evs[i], evs[i + 1]);
+      cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
+      st->ms_reduce += b; st->ms_score += c;
+    }
+    for (size_t i = 0; i + 1 < evl.size(); i += 2) {
+      float a = 0;
+      cudaEventElapsedTime(&a, evl[i], evl[i + 1]);
+      st->ms_labels += a;  // on the label stream: overlaps ms_reduce / ms_score when pipelined
     }
     if (evs.size() >= 2) {
       float d = 0;
@@ -809,14 +901,9 @@ int scdc_draw_labels(scdc_handle* h, uint64_t seed, int64_t perm_offset, int64_t
   CU(bits1.alloc((size_t)N * (B / 32)));
   CU(dct.alloc((size_t)B * N));
   CU(dcond.alloc((size_t)B * N));
-  const int nt = 32;
-  const size_t smem = (size_t)((C == 2) ? 4 * T : T) * nt * sizeof(uint32_t);
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(scdc::k_draw_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int64_t done = 0; done < n; done += B) {
     const int nb = (int)std::min<int64_t>(B, n - done);
-    scdc::k_draw_labels<<<B / nt, nt, smem, s>>>(N, T, C, h->ct.p, h->urn_init.p, seed, perm_offset + done, B, 1, bits1.p,
-                                                  lab2.p, dcond.p, dct.p);
-    CU(cudaGetLastError());
+    CU(launch_draw(h, s, seed, perm_offset + done, B, 1, bits1.p, lab2.p, dcond.p, dct.p));
     CU(cudaMemcpyAsync(ct_out + (size_t)done * N, dct.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));
     if (cond_out && C == 2)
       CU(cudaMemcpyAsync(cond_out + (size_t)done * N, dcond.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));

@@ -20,56 +20,49 @@
 namespace scdc {
 
 // ------------------------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11). counter = (draw block j, 0, replicate lo, replicate hi), key = seed.
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: block(visit i, j) has counter (i, j, replicate lo, replicate hi)
+// and key = seed. Draw d (0 = condition, 1 = cell type) of visit i, attempt a, is word 2a + d of the visit's stream
+// (block j = (2a + d) / 4, element (2a + d) % 4): every draw is a pure function of (seed, replicate, visit, attempt),
+// so the generator has no sequential state and any replicate range can be regenerated anywhere.
 // ------------------------------------------------------------------------------------------------------------------
-struct Philox {
-  uint32_t c0, c1, c2, c3, k0, k1;
-  uint32_t out[4];
-  int have;
-  __host__ __device__ Philox(uint64_t seed, uint64_t replicate)
-      : c0(0), c1(0), c2((uint32_t)replicate), c3((uint32_t)(replicate >> 32)), k0((uint32_t)seed),
-        k1((uint32_t)(seed >> 32)), have(0) {}
-  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-    uint64_t p = (uint64_t)a * b;
-    hi = (uint32_t)(p >> 32);
-    lo = (uint32_t)p;
-  }
-  __host__ __device__ inline void refill() {
-    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      uint32_t hi0, lo0, hi1, lo1;
-      mulhilo(0xD2511F53u, x0, hi0, lo0);
-      mulhilo(0xCD9E8D57u, x2, hi1, lo1);
-      uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
-      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-      a += 0x9E3779B9u;
-      b += 0xBB67AE85u;
-    }
-    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
-    have = 4;
-    if (++c0 == 0) ++c1;
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t y0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, y1 = (uint32_t)p1, y2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, y3 = (uint32_t)p0;
+    c0 = y0; c1 = y1; c2 = y2; c3 = y3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
   }
-  __host__ __device__ inline uint32_t next() {
-    if (have == 0) refill();
-    uint32_t v = out[4 - have];  // consumed in order out[0..3]
-    --have;
-    return v;
-  }
-  // uniform integer in [0, range), range >= 1; Lemire's multiply-shift with rejection (exactly unbiased)
-  __host__ __device__ inline uint32_t bounded(uint32_t range) {
-    uint64_t m = (uint64_t)next() * range;
-    uint32_t l = (uint32_t)m;
-    if (l < range) {
-      uint32_t t = (0u - range) % range;
-      while (l < t) {
-        m = (uint64_t)next() * range;
-        l = (uint32_t)m;
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform integer in [0, range): Lemire's multiply-shift with rejection (exactly unbiased). blk0 = block (visit, 0).
+__host__ __device__ inline uint32_t bounded_draw(const uint32_t blk0[4], int d, uint32_t range, uint32_t visit, uint32_t r_lo,
+                                                 uint32_t r_hi, uint32_t k0, uint32_t k1) {
+  uint64_t m = (uint64_t)blk0[d] * range;
+  uint32_t l = (uint32_t)m;
+  if (l < range) {
+    const uint32_t t = (0u - range) % range;
+    int a = 0;
+    while (l < t) {  // rejected (probability < range / 2^32): next attempt's word
+      ++a;
+      const int w = 2 * a + d;
+      uint32_t x;
+      if (w < 4) {
+        x = blk0[w];
+      } else {
+        uint32_t o[4];
+        philox4x32_10(visit, (uint32_t)(w >> 2), r_lo, r_hi, k0, k1, o);
+        x = o[w & 3];
       }
+      m = (uint64_t)x * range;
+      l = (uint32_t)m;
     }
-    return (uint32_t)(m >> 32);
   }
-};
+  return (uint32_t)(m >> 32);
+}
 
 // byte offset of replicate q's label inside one cell's label row (row length Bpad bytes), J replicates per lane
 __host__ __device__ inline int lab2_offset(int q, int J) {
@@ -78,62 +71,114 @@ __host__ __device__ inline int lab2_offset(int q, int J) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K1: one thread = one replicate; sequential urn draws over the cells (a uniformly random arrangement of a multiset
-// revealed cell by cell: next label k with probability remaining[k] / remaining total). Fenwick trees live in shared
-// memory, laid out [node][thread] so a warp never bank-conflicts.
-//   detection   : ct' = global shuffle of cell types                    (R/utils_permutation.R:509)
+// K1: one thread = one replicate; sequential urn draws over the cells: a uniformly random arrangement of a multiset
+// revealed cell by cell (next label k with probability remaining[k] / remaining total) — the distribution of
+// base::sample on the same strata.
+//   detection   : ct' = global shuffle of cell types                    (reference R/utils_permutation.R:509)
 //   differential: cond' = shuffle of conditions inside each cell type   (:536-541)
 //                 ct'   = shuffle of cell types inside each cond' class (:552-569)
+// Cells are visited in `visit` order (differential: stably sorted by cell type, so the condition urn of the current
+// cell type is two registers; detection: cell order). The cell-type urn is two-level: NG group sums (8 labels per
+// group) in registers, the per-label remaining counts in shared memory laid out [label][thread] (bank = lane).
+// Philox blocks depend only on (seed, replicate, visit), so they are computed off the urn's dependency chain.
 // outputs: bits1[cell][Bpad/32] (bit q%32 of word q/32 = cond' of replicate q), lab2[cell][Bpad] (group code
-// cond' * T + ct' in the K2b layout). Optional row-major debug copies for scdc_draw_labels.
+// cond' * T + ct' in the K2b layout). Optional replicate-major debug copies for scdc_draw_labels.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_draw_labels(int N, int T, int C, const uint8_t* __restrict__ ct, const uint32_t* __restrict__ init,
-                              uint64_t seed, int64_t perm0, int Bpad, int J, uint32_t* __restrict__ bits1,
-                              uint8_t* __restrict__ lab2, uint8_t* __restrict__ dbg_cond, uint8_t* __restrict__ dbg_ct) {
-  extern __shared__ uint32_t sm_u32[];
-  const int nt = blockDim.x, tx = threadIdx.x;
-  const int q = blockIdx.x * nt + tx;  // replicate inside the batch (always < Bpad: Bpad % blockDim == 0)
-  // state rows: differential: rem[c][t] (2T rows) then tree[c][1..T] (2T rows) ; detection: tree[1..T] (T rows)
-  const int n_state = (C == 2) ? 4 * T : T;
-  for (int i = 0; i < n_state; ++i) sm_u32[i * nt + tx] = init[i];
-  uint32_t tot2[2] = {init[n_state], init[n_state + 1]};
-#define ST(i) sm_u32[(i) * nt + tx]
-  Philox rng(seed, (uint64_t)(perm0 + q));
-  int top = 1;
-  while (top * 2 <= T) top *= 2;
+template <int NG>
+__global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const int* __restrict__ visit,
+                                                    const int* __restrict__ ct_seg, const uint32_t* __restrict__ ngroup_u,
+                                                    uint64_t seed, int64_t perm0, int Bpad, int J,
+                                                    uint32_t* __restrict__ bits1, uint8_t* __restrict__ lab2,
+                                                    uint8_t* __restrict__ dbg_cond, uint8_t* __restrict__ dbg_ct) {
+  extern __shared__ uint32_t sm_u32[];  // [C][NG*8][32]
+  const int tx = threadIdx.x;
+  const int q = blockIdx.x * 32 + tx;  // replicate inside the batch (Bpad % 32 == 0)
+  const uint64_t rep = (uint64_t)(perm0 + q);
+  const uint32_t r_lo = (uint32_t)rep, r_hi = (uint32_t)(rep >> 32), k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t gs[2][NG], tot[2] = {0, 0};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      uint32_t sum = 0;
+      for (int k = 0; k < 8; ++k) {
+        const int lab = j * 8 + k;
+        const uint32_t n = (c < C && lab < T) ? ngroup_u[c * T + lab] : 0u;
+        if (c < C) sm_u32[((c * NG * 8) + lab) * 32 + tx] = n;
+        sum += n;
+      }
+      gs[c][j] = sum;
+      tot[c] += sum;
+    }
+  }
   const int Bw = Bpad / 32;
   const int off2 = lab2_offset(q, J);
-  for (int i = 0; i < N; ++i) {
-    int c = 0;
-    int tree0 = 0;  // first row of the Fenwick tree to draw from
-    if (C == 2) {
-      int t = ct[i];
-      uint32_t r0 = ST(t), r1 = ST(T + t);
-      uint32_t u = rng.bounded(r0 + r1);
-      c = (u < r0) ? 0 : 1;
-      ST(c * T + t) -= 1;
-      tree0 = 2 * T + c * T;
-    }
-    uint32_t u = rng.bounded(tot2[c]);
-    tot2[c] -= 1;
-    int pos = 0;
-    for (int step = top; step > 0; step >>= 1) {
-      int nxt = pos + step;
-      if (nxt <= T) {
-        uint32_t w = ST(tree0 + nxt - 1);
-        if (w <= u) { pos = nxt; u -= w; }
+  uint32_t blk[4];
+  philox4x32_10(0u, 0u, r_lo, r_hi, k0, k1, blk);
+  int v = 0;
+  const int n_seg = (C == 2) ? T : 1;
+  for (int t = 0; t < n_seg; ++t) {
+    const int v_end = (C == 2) ? ct_seg[t + 1] : N;
+    uint32_t r0 = 0, r1 = 0;
+    if (C == 2) { r0 = ngroup_u[t]; r1 = ngroup_u[T + t]; }
+    for (; v < v_end; ++v) {
+      uint32_t nxt[4];
+      philox4x32_10((uint32_t)(v + 1), 0u, r_lo, r_hi, k0, k1, nxt);  // next visit's block, off the critical path
+      const int cell = visit ? visit[v] : v;
+      int c = 0;
+      if (C == 2) {
+        const uint32_t u = bounded_draw(blk, 0, r0 + r1, (uint32_t)v, r_lo, r_hi, k0, k1);
+        c = (u < r0) ? 0 : 1;
+        if (c) --r1; else --r0;
       }
+      uint32_t u = bounded_draw(blk, 1, tot[c], (uint32_t)v, r_lo, r_hi, k0, k1);
+      tot[c] -= 1;
+      // level 1: group
+      int grp = NG - 1;
+      uint32_t run = 0, base = 0;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < NG; ++j) {
+        const uint32_t g = c ? gs[1][j] : gs[0][j];
+        const uint32_t nr = run + g;
+        if (!found && u < nr) { grp = j; base = run; found = true; }
+        run = nr;
+      }
+      u -= base;
+      // level 2: label inside the group
+      uint32_t* cp = sm_u32 + ((c * NG * 8) + grp * 8) * 32 + tx;
+      uint32_t n8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) n8[k] = cp[k * 32];
+      int kk = 7;
+      run = 0;
+      found = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t nr = run + n8[k];
+        if (!found && u < nr) { kk = k; found = true; }
+        run = nr;
+      }
+      uint32_t nsel = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nsel = (k == kk) ? n8[k] : nsel;
+      cp[kk * 32] = nsel - 1;
+#pragma unroll
+      for (int j = 0; j < NG; ++j) {
+        if (j == grp) { if (c) --gs[1][j]; else --gs[0][j]; }
+      }
+      const int pos = grp * 8 + kk;
+      if (C == 2) {
+        const uint32_t word = __ballot_sync(0xffffffffu, c == 1);
+        if (tx == 0) bits1[(size_t)cell * Bw + (q >> 5)] = word;
+      }
+      lab2[(size_t)cell * Bpad + off2] = (uint8_t)(c * T + pos);
+      if (dbg_ct) dbg_ct[(size_t)q * N + cell] = (uint8_t)pos;
+      if (dbg_cond) dbg_cond[(size_t)q * N + cell] = (uint8_t)c;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) blk[w] = nxt[w];
     }
-    for (int k = pos + 1; k <= T; k += k & (-k)) ST(tree0 + k - 1) -= 1;
-    if (C == 2) {
-      uint32_t word = __ballot_sync(0xffffffffu, c == 1);
-      if ((tx & 31) == 0) bits1[(size_t)i * Bw + (q >> 5)] = word;
-    }
-    lab2[(size_t)i * Bpad + off2] = (uint8_t)(c * T + pos);
-    if (dbg_ct) dbg_ct[(size_t)q * N + i] = (uint8_t)pos;
-    if (dbg_cond) dbg_cond[(size_t)q * N + i] = (uint8_t)c;
   }
-#undef ST
 }
 
 // ------------------------------------------------------------------------------------------------------------------

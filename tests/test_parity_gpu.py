@@ -63,6 +63,22 @@ def test_device_philox_labels_match_cpu_restatement(liver_cases, mode):
         assert np.array_equal(cond, cond_o)
 
 
+@pytest.mark.parametrize("kw", [
+    dict(n_cells=4000, n_genes=30, n_celltypes=30, n_conditions=2, n_lri=40, seed=11, min_group=10),    # NG = 4
+    dict(n_cells=8000, n_genes=30, n_celltypes=60, n_conditions=2, n_lri=40, seed=12, min_group=10),    # NG = 8
+    dict(n_cells=6000, n_genes=20, n_celltypes=100, n_conditions=1, n_lri=30, seed=13, min_group=10),   # NG = 16
+    dict(n_cells=9000, n_genes=20, n_celltypes=200, n_conditions=1, n_lri=30, seed=14, min_group=10),   # NG = 32
+])
+def test_device_philox_labels_match_cpu_restatement_all_urn_widths(kw):
+    prob, ai, simple, mask = synthetic.make_problem(kw)
+    with Engine(prob) as eng:
+        cond, ct = eng.draw_labels(40, seed=kw["seed"], perm_offset=2**33 + 5)   # 64-bit replicate index
+    cond_o, ct_o = oracle_c.philox_labels(prob, 40, seed=kw["seed"], perm_offset=2**33 + 5)
+    assert np.array_equal(ct, ct_o)
+    if cond is not None:
+        assert np.array_equal(cond, cond_o)
+
+
 @pytest.mark.parametrize("mode", ["cond", "nocond"])
 def test_device_generated_run_equals_oracle_on_the_same_labels(liver_cases, mode):
     """Philox mode end to end: counts from on-device labels == oracle counts on the CPU restatement of those labels,
@@ -77,6 +93,19 @@ def test_device_generated_run_equals_oracle_on_the_same_labels(liver_cases, mode
         b = eng.run(n - 200, seed=seed, perm_offset=200)["counts"]
     assert np.array_equal(whole, want, equal_nan=True)
     assert np.array_equal(np.nan_to_num(a) + np.nan_to_num(b), np.nan_to_num(want))
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+def test_label_super_batches_and_pipelining_do_not_change_counts(liver_cases, mode, monkeypatch):
+    """Labels are drawn per super-batch (normally one); with several, K1 runs one ahead on a second stream."""
+    prob = liver_cases[mode]["prob"]
+    with Engine(prob) as eng:
+        whole = eng.run(1000, seed=5, batch_size=128)["counts"]
+        monkeypatch.setenv("SCDC_SUPER_BATCH", "256")
+        piped = eng.run(1000, seed=5, batch_size=128)["counts"]
+        monkeypatch.setenv("SCDC_SUPER_BATCH", "128")
+        piped2 = eng.run(1000, seed=5, batch_size=128)["counts"]
+    assert np.array_equal(whole, piped, equal_nan=True) and np.array_equal(whole, piped2, equal_nan=True)
 
 
 def test_uploaded_labels_that_are_not_stratified_shuffles_are_rejected(liver_cases):
