@@ -395,7 +395,7 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
   J = env_int("SCDC_J", J);
   if (J != 1 && J != 2 && J != 4) J = 1;
   while (J > 1 && (Bpad % (32 * J)) != 0) J >>= 1;
-  const size_t per_warp = (size_t)K * J * 256 + 512;
+  const size_t per_warp = (size_t)K * J * 256 + 1024;
   const int nCJ = Bpad / (32 * J);
   const size_t cap = h->smem_optin ? h->smem_optin : 232448;
   int bestW = 1, best_warps = 0, best_bps = 1;
@@ -417,7 +417,7 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
 template <int J>
 cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
                            cudaStream_t s) {
-  auto kern = scdc::k_scatter<J>;
+  auto kern = scdc::k_scatter<J, 8>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
@@ -514,10 +514,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   int64_t launches = 0, reduce_launches = 0;
   double reduce_bytes = 0;
   const double sv = 8.0;
-  cudaEvent_t ev_begin = nullptr;
   CU(mark(evs, s));  // evs[0]: start of the whole loop on the compute stream
-  ev_begin = evs[0];
-  (void)ev_begin;
   auto issue_labels = [&](int64_t sb_start, int buf) -> int {
     if (pipelined && freed_set[buf]) CU(cudaStreamWaitEvent(sL, freed[buf], 0));
     CU(mark(evl, sL));
@@ -893,7 +890,7 @@ int scdc_draw_labels(scdc_handle* h, uint64_t seed, int64_t perm_offset, int64_t
   if (n < 1 || perm_offset < 0) return fail(SCDC_EINVAL, "n must be >= 1 and perm_offset >= 0");
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-  const int N = h->N, T = h->T, C = h->C;
+  const int N = h->N, C = h->C;
   const int B = 128;
   DBuf<uint8_t> lab2, dct, dcond;
   DBuf<uint32_t> bits1;

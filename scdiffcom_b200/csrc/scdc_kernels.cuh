@@ -313,16 +313,16 @@ __global__ void __launch_bounds__(256) k_pass1_cond(int G, int T, int nWC, const
 // is a multiple of 32 banks and the column index is the lane, so the read-modify-write is conflict-free and needs no
 // atomics whatever the labels are. lab2 layout: [cell][Bpad] bytes, lane's J labels adjacent (one J-byte load).
 // M2 layout: [chunk32][gene][k][32 lanes], value = sum / n_k.
-// grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K*J*32*8 + 512).
+// grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K*J*32*8 + 1024).
 // ------------------------------------------------------------------------------------------------------------------
 template <int J> struct LabWord;
 template <> struct LabWord<1> { typedef uint8_t type; };
 template <> struct LabWord<2> { typedef uint16_t type; };
 template <> struct LabWord<4> { typedef uint32_t type; };
 
-template <int J>
+template <int J, int U>
 __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
-                          const double* __restrict__ values, const uint8_t* __restrict__ lab2, int Bpad,
+                          const double* __restrict__ values, const uint8_t* __restrict__ lab2, int lab_stride,
                           const double* __restrict__ ngroup, const int* __restrict__ gene_order, double* __restrict__ M2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef typename LabWord<J>::type lab_t;
@@ -330,41 +330,60 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   const int cJ = blockIdx.y * W + warp;
   if (cJ >= nCJ) return;
   const int g = gene_order[blockIdx.x];
-  uint4* stage = reinterpret_cast<uint4*>(smem_raw) + warp * 32;
-  double* acc = reinterpret_cast<double*>(smem_raw + (size_t)W * 512) + (size_t)warp * K * J * 32 + lane;
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw) + warp * 64;  // two buffers of 32 entries
+  double* acc = reinterpret_cast<double*>(smem_raw + (size_t)W * 1024) + (size_t)warp * K * J * 32 + lane;
   for (int i = 0; i < K * J; ++i) acc[i * 32] = 0.0;
   const int beg = colptr[g], end = colptr[g + 1];
+  const int nst = (end - beg + 31) >> 5;
   const uint8_t* labbase = lab2 + (size_t)cJ * 32 * J + lane * J;
-  constexpr int U = 4;
+  // The labels of the NEXT group of U entries are loaded (L2 latency) while the CURRENT group is accumulated, and the
+  // entries two stages ahead are in flight from global memory: the read-modify-write chain never waits on a load.
   int cell_n = 0;
   double v_n = 0.0;
   if (beg + lane < end) { cell_n = rowidx[beg + lane]; v_n = values[beg + lane]; }
-  for (int e0 = beg; e0 < end; e0 += 32) {
-    __syncwarp();
-    stage[lane] = pack_entry(cell_n, v_n);
-    __syncwarp();
-    {  // prefetch the next 32 entries while this stage is consumed; padding entries add +0.0 to cell 0's group
-      int e = e0 + 32 + lane;
-      cell_n = 0;
-      v_n = 0.0;
+  stage[lane] = pack_entry(cell_n, v_n);
+  cell_n = 0; v_n = 0.0;  // padding entries add +0.0 to cell 0's group: bit-neutral
+  if (beg + 32 + lane < end) { cell_n = rowidx[beg + 32 + lane]; v_n = values[beg + 32 + lane]; }
+  __syncwarp();
+  double valN[U];
+  lab_t lbN[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint4 en = stage[u];
+    valN[u] = entry_value(en);
+    lbN[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en.x * lab_stride);
+  }
+  for (int s = 0; s < nst; ++s) {
+    uint4* cur_buf = stage + (s & 1) * 32;
+    uint4* nxt_buf = stage + ((s + 1) & 1) * 32;
+    __syncwarp();  // every lane is done reading stage s-1 from nxt_buf
+    nxt_buf[lane] = pack_entry(cell_n, v_n);
+    {
+      const int e = beg + (s + 2) * 32 + lane;
+      cell_n = 0; v_n = 0.0;
       if (e < end) { cell_n = rowidx[e]; v_n = values[e]; }
     }
-#pragma unroll 1
-    for (int i = 0; i < 32; i += U) {
-      uint4 en[U];
+    __syncwarp();
+#pragma unroll
+    for (int gq = 0; gq < 32 / U; ++gq) {
+      double val[U];
       lab_t lb[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) en[u] = stage[i + u];
-#pragma unroll
-      for (int u = 0; u < U; ++u) lb[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en[u].x * Bpad);
+      for (int u = 0; u < U; ++u) { val[u] = valN[u]; lb[u] = lbN[u]; }
+      const uint4* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const double val = entry_value(en[u]);
+        const uint4 en = src[u];
+        valN[u] = entry_value(en);
+        lbN[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en.x * lab_stride);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         double cur[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) cur[j] = acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32];
 #pragma unroll
-        for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val;
+        for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val[u];
       }
     }
   }
