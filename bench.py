@@ -160,7 +160,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from scdiffcom_b200 import Engine, device_count, perm_counts
+    from scdiffcom_b200 import Engine, device_count, perm_counts, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,12 +191,11 @@ def run_ours(args):
     stats_acc = []
 
     def step(collect):
-        r = eng.run(iters, seed=seed, perm_offset=rank * iters, counts_device_ptr=counts_dev.data_ptr(),
-                    want_host_counts=False, stream=stream.cuda_stream, batch_size=args.batch)
-        if world > 1:
-            dist.all_reduce(counts_dev)
+        # weak scaling: the job at `world` GPUs is world * iters replicates; rank r runs [r * iters, (r + 1) * iters)
+        st = sharding.run_sharded(eng, world * iters, counts_dev, seed=seed, batch_size=args.batch,
+                                  stream=stream.cuda_stream)
         if collect:
-            stats_acc.append(r["stats"])
+            stats_acc.append(st)
 
     for _ in range(args.warmup):
         step(False)

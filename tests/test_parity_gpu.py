@@ -175,3 +175,20 @@ def test_device_shuffles_are_uniform(liver_cases):
     expect = (nt * (nt - 1)).sum() / (N * (N - 1))
     same = (ct[:, :-1] == ct[:, 1:]).mean()
     assert abs(same - expect) < 5 * np.sqrt(expect * (1 - expect) / (n * (N - 1)))
+
+
+def test_in_library_multi_gpu_equals_single_gpu(liver_cases):
+    """scdc_perm_counts with n_gpus = 2: host thread per device, replicate ranges, ncclAllReduce of the counters."""
+    from scdiffcom_b200 import device_count
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    for mode in ("cond", "nocond"):
+        prob = liver_cases[mode]["prob"]
+        one = perm_counts(prob, 1000, seed=3, n_gpus=1)
+        two = perm_counts(prob, 1000, seed=3, n_gpus=2)
+        assert two["stats"]["n_gpus"] == 2
+        assert np.array_equal(one["counts"], two["counts"], equal_nan=True)
+        pcond, pct = helpers.reference_like_labels(prob, 300, 4)
+        a = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=1)["counts"]
+        b = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=2)["counts"]
+        assert np.array_equal(a, b, equal_nan=True)
