@@ -203,13 +203,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
         step(True)
-    ev1.record(stream)
+        evs[k + 1].record(stream)
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -278,7 +279,7 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_upload": e2e_stats["ms_upload"], "ms_device": e2e_stats["ms_device"]},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats_acc)),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "device_ms": shares, "counts_checksum": checksum,
+            "device_ms": shares, "step_ms": step_ms, "counts_checksum": checksum,
         }
         print(json.dumps(line))
     eng.close()
