@@ -94,7 +94,7 @@ struct scdc_handle {
   // K3 v2: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
   DBuf<double> thr;
-  int n_tasks = 0;
+  int n_tasks = 0, score_threads = 256;
   // per-run workspace (grown on demand)
   DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
@@ -325,7 +325,8 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
     std::vector<int> srow(h->R), t_lri, t_beg, t_end;
     for (int r = 0; r < h->R; ++r) srow[r] = r;
     std::stable_sort(srow.begin(), srow.end(), [&](int a, int b) { return p->row_lri[a] < p->row_lri[b]; });
-    const int rpb = kScoreThreads * kScoreRPT;
+    h->score_threads = kScoreThreads;  // (64/128-thread blocks were measured slower on configs 2 and 3)
+    const int rpb = h->score_threads * kScoreRPT;
     for (int b = 0; b < h->R;) {
       int e = b;
       while (e < h->R && p->row_lri[srow[e]] == p->row_lri[srow[b]]) ++e;
@@ -591,7 +592,8 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       A.nChunks = (nb + 31) / 32; A.n_valid = nb; A.R = R;
       const int n_arr = (C == 2) ? 8 + h->nS : 2;
       int P = 32;
-      while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > 100 * 1024) P >>= 1;
+      const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", 100) * 1024;
+      while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > smem_target) P >>= 1;
       P = env_int("SCDC_SCORE_P", P);
       A.P = P;
       const size_t smem = (size_t)n_arr * P * A.Tp * 8;
@@ -601,11 +603,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       if (C == 2) {
         auto kern = scdc::k_score_v2<2, kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, kScoreThreads, smem, s>>>(A);
+        kern<<<h->n_tasks, h->score_threads, smem, s>>>(A);
       } else {
         auto kern = scdc::k_score_v2<1, kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, kScoreThreads, smem, s>>>(A);
+        kern<<<h->n_tasks, h->score_threads, smem, s>>>(A);
       }
       CU(cudaGetLastError());
       ++launches;

@@ -576,40 +576,60 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
       if (pbase >= A.n_valid) break;
       __syncthreads();
       // ---------------- stage A ----------------
-      for (int item = tid; item < 2 * T * P; item += nthr) {
-        const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
-        const int s0 = side ? nL : 0, s1 = side ? nS : nL;
-        const size_t lane_off = (size_t)hf * P + p;
-        if (C == 1) {
-          double m = 0.0;
-          bool h = false;
-          for (int s = s0; s < s1; ++s) {
+      const int n_items = 2 * T * P;
+      if (C == 1) {
+        for (int item = tid; item < n_items; item += nthr) {
+          const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+          const int s0 = side ? nL : 0, s1 = side ? nS : nL;
+          const size_t lane_off = (size_t)hf * P + p;
+          double m = A.M2[(((size_t)ch * A.G + s_gs[s0]) * K + ct) * 32 + lane_off];  // LIGAND_1 / RECEPTOR_1: always present
+          for (int s = s0 + 1; s < s1; ++s) {
             const int g = s_gs[s];
-            if (g >= 0) {
-              double v = A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane_off];
-              m = h ? fmin(m, v) : v;
-              h = true;
-            }
+            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane_off]);
           }
           sm_d[side * tile + p * Tp + ct] = m;
-        } else {
-          double m10 = 0.0, m11 = 0.0, m20 = 0.0, m21 = 0.0;
-          bool h = false;
-          for (int s = s0; s < s1; ++s) {
-            const int g = s_gs[s];
-            double d = 0.0;
-            if (g >= 0) {
-              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane_off, i1 = i0 + (size_t)T * 32;
-              const double v10 = A.M1[i0], v11 = A.M1[i1], v20 = A.M2[i0], v21 = A.M2[i1];
-              d = v11 - v10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
-              m10 = h ? fmin(m10, v10) : v10; m11 = h ? fmin(m11, v11) : v11;
-              m20 = h ? fmin(m20, v20) : v20; m21 = h ? fmin(m21, v21) : v21;
-              h = true;
-            }
-            sm_d[(8 + s) * tile + p * Tp + ct] = d;
+        }
+      } else {
+        // two items per iteration, first-subunit loads of both issued before any use (the means are not L2-resident:
+        // memory-level parallelism matters); extra subunits of a complex are rare and handled after
+        for (int item0 = tid; item0 < n_items; item0 += 2 * nthr) {
+          double v10[2], v11[2], v20[2], v21[2];
+          int pp[2], cc[2], sd[2];
+          bool ok[2];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int item = item0 + w * nthr;
+            ok[w] = item < n_items;
+            const int it = ok[w] ? item : item0;
+            pp[w] = it % P;
+            const int rest = it / P;
+            cc[w] = rest % T;
+            sd[w] = rest / T;
+            const int g = s_gs[sd[w] ? nL : 0];
+            const size_t i0 = (((size_t)ch * A.G + g) * K + cc[w]) * 32 + (size_t)hf * P + pp[w], i1 = i0 + (size_t)T * 32;
+            v10[w] = A.M1[i0]; v11[w] = A.M1[i1]; v20[w] = A.M2[i0]; v21[w] = A.M2[i1];
           }
-          double* base = sm_d + side * 2 * tile + p * Tp + ct;  // arrays: pass*4 + side*2 + cond
-          base[0] = m10; base[tile] = m11; base[4 * tile] = m20; base[5 * tile] = m21;
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            if (!ok[w]) continue;
+            const int p = pp[w], ct = cc[w], side = sd[w];
+            const int s0 = side ? nL : 0, s1 = side ? nS : nL;
+            double m10 = v10[w], m11 = v11[w], m20 = v20[w], m21 = v21[w];
+            sm_d[(8 + s0) * tile + p * Tp + ct] = v11[w] - v10[w];  // cond2 - cond1 (reference R/utils_cci.R:212-239)
+            for (int s = s0 + 1; s < s1; ++s) {
+              const int g = s_gs[s];
+              double d = 0.0;
+              if (g >= 0) {
+                const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + (size_t)hf * P + p, i1 = i0 + (size_t)T * 32;
+                const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
+                d = a11 - a10;
+                m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
+              }
+              sm_d[(8 + s) * tile + p * Tp + ct] = d;
+            }
+            double* base = sm_d + side * 2 * tile + p * Tp + ct;  // arrays: pass*4 + side*2 + cond
+            base[0] = m10; base[tile] = m11; base[4 * tile] = m20; base[5 * tile] = m21;
+          }
         }
       }
       __syncthreads();
