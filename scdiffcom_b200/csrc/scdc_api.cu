@@ -45,6 +45,18 @@ double now_ms() {
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+struct PhaseTimer {  // SCDC_TIMING=1: host-side phase times on stderr
+  bool on;
+  double t;
+  PhaseTimer() : on(getenv("SCDC_TIMING") != nullptr), t(now_ms()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const double n = now_ms();
+    fprintf(stderr, "[scdc timing] %-28s %8.2f ms\n", what, n - t);
+    t = n;
+  }
+};
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -81,7 +93,7 @@ struct scdc_handle {
   int device = 0;
   int N = 0, G = 0, T = 0, C = 0, L = 0, R = 0, nL = 0, nR = 0, K = 0, ncols = 0, nS = 0;
   size_t nnz = 0;
-  cudaStream_t stream = nullptr, stream_labels = nullptr;
+  cudaStream_t stream = nullptr, stream_labels = nullptr, stream_score = nullptr;
   int num_sms = 148;
   size_t smem_optin = 0;
   // problem
@@ -98,7 +110,7 @@ struct scdc_handle {
   // per-run workspace (grown on demand)
   DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
-  DBuf<double> M1, M2, dist;
+  DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
   DBuf<int> flag;
   double ms_upload = 0;
 };
@@ -190,17 +202,6 @@ int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* 
   return SCDC_OK;
 }
 
-// smallest y with sqrt_rn(y) >= o: (sqrt(x) >= o) == (x >= y) for every x, because sqrt_rn is monotone non-decreasing
-double product_threshold(double o) {
-  if (std::isnan(o)) return o;
-  if (o <= 0.0) return 0.0;  // sqrt(x) >= o for every x >= 0; x < 0 gives NaN on both sides (false)
-  if (std::isinf(o)) return o;
-  double y = o * o;
-  while (y > 0.0 && std::sqrt(std::nextafter(y, -INFINITY)) >= o) y = std::nextafter(y, -INFINITY);
-  while (std::sqrt(y) < o) y = std::nextafter(y, INFINITY);
-  return y;
-}
-
 constexpr int kScoreThreads = 256, kScoreRPT = 2;
 
 }  // namespace
@@ -216,14 +217,17 @@ void scdc_release(scdc_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_labels) cudaStreamDestroy(h->stream_labels);
+  if (h->stream_score) cudaStreamDestroy(h->stream_score);
   delete h;
 }
 
-int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
+static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, bool validated) {
   if (!out) return fail(SCDC_EINVAL, "out is NULL");
   *out = nullptr;
-  int rc = validate_problem(p);
+  PhaseTimer pt;
+  int rc = validated ? SCDC_OK : validate_problem(p);
   if (rc) return rc;
+  pt.lap("create: validate");
   std::vector<int> ids;
   if (count_sm100_devices(&ids) == 0)
     return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
@@ -244,6 +248,7 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&h->stream_labels, cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&h->stream_score, cudaStreamNonBlocking, lo));
   }
   int v = 0;
   CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
@@ -281,6 +286,7 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
       CU(h->ct_seg.upload(ct_seg.data(), ct_seg.size(), s));
     }
     CU(h->colptr.upload(p->colptr, (size_t)G + 1, s));
+    pt.lap("create: context + small prep");
     CU(h->rowidx.upload(p->rowidx, h->nnz, s));
     CU(h->values.upload(p->values, h->nnz, s));
     CU(h->ct.upload(ct8.data(), N, s));
@@ -295,6 +301,7 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
     CU(h->obs.upload(p->observed, (size_t)h->R * h->ncols, s));
     h->obs_na.resize((size_t)h->R * h->ncols);
     for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(p->observed[i]) ? 1 : 0;
+    pt.lap("create: enqueue uploads");
     std::vector<int> segptr, rows_s;
     std::vector<double> vals_s;
     if (C == 2) {
@@ -322,9 +329,14 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
       CU(h->values_s.upload(vals_s.data(), h->nnz, s));
     }
     // K3 v2 work list: rows stably sorted by LRI, each LRI cut into slices of kScoreThreads * kScoreRPT rows
+    pt.lap("create: pass-1 matrix copy");
     std::vector<int> srow(h->R), t_lri, t_beg, t_end;
-    for (int r = 0; r < h->R; ++r) srow[r] = r;
-    std::stable_sort(srow.begin(), srow.end(), [&](int a, int b) { return p->row_lri[a] < p->row_lri[b]; });
+    {  // counting sort by LRI (stable)
+      std::vector<int> start((size_t)h->L + 1, 0);
+      for (int r = 0; r < h->R; ++r) ++start[(size_t)p->row_lri[r] + 1];
+      for (int l = 0; l < h->L; ++l) start[(size_t)l + 1] += start[l];
+      for (int r = 0; r < h->R; ++r) srow[start[p->row_lri[r]]++] = r;
+    }
     h->score_threads = kScoreThreads;  // (64/128-thread blocks were measured slower on configs 2 and 3)
     const int rpb = h->score_threads * kScoreRPT;
     for (int b = 0; b < h->R;) {
@@ -338,17 +350,21 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
       b = e;
     }
     h->n_tasks = (int)t_lri.size();
-    std::vector<double> thr((size_t)h->R * C);
-    for (int c = 0; c < C; ++c)
-      for (int r = 0; r < h->R; ++r)
-        thr[(size_t)c * h->R + r] = product_threshold(p->observed[(size_t)(C == 2 ? 1 + c : 0) * h->R + r]);
+    pt.lap("create: K3 work list");
+    CU(h->thr.alloc((size_t)h->R * C + 1));
+    if (h->R > 0) {  // product thresholds of the one-sided geometric columns, computed on the device (IEEE sqrt)
+      scdc::k_product_thresholds<<<(unsigned)(((size_t)h->R * C + 255) / 256), 256, 0, s>>>(
+          (size_t)h->R * C, h->obs.p + (C == 2 ? (size_t)h->R : 0), h->thr.p);
+      CU(cudaGetLastError());
+    }
     CU(h->srow.upload(srow.data(), srow.size(), s));
     CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
     CU(h->task_beg.upload(t_beg.data(), t_beg.size(), s));
     CU(h->task_end.upload(t_end.data(), t_end.size(), s));
-    CU(h->thr.upload(thr.data(), thr.size(), s));
     CU(h->flag.alloc(1));
+    pt.lap("create: enqueue rest");
     CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+    pt.lap("create: wait for H2D");
   } catch (const std::bad_alloc&) {
     return fail(SCDC_ENOMEM, "host allocation failed while staging the problem");
   }
@@ -356,6 +372,8 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) {
   *out = h.release();
   return SCDC_OK;
 }
+
+int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) { return create_impl(p, device, out, false); }
 
 }  // extern "C"
 
@@ -417,14 +435,14 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
 
 template <int J>
 cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                           cudaStream_t s) {
+                           double* M2, cudaStream_t s) {
   auto kern = scdc::k_scatter<J, 8>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
   dim3 grid(h->G, (nCJ + pl.W - 1) / pl.W);
   kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
-                                        h->ngroup.p, h->gene_order.p, h->M2.p);
+                                        h->ngroup.p, h->gene_order.p, M2);
   return cudaGetLastError();
 }
 
@@ -478,8 +496,15 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(h->lab2[i].ensure((size_t)N * SB));
     if (C == 2) CU(h->bits1[i].ensure((size_t)N * SBw));
   }
-  if (C == 2) CU(h->M1.ensure(msz));
-  CU(h->M2.ensure(msz));
+  // K3 (issue-bound) of batch b runs on its own stream next to K2 (shared-memory-pipe-bound) of batch b + 1
+  // (measured: no gain on configs 2/3 — both kernels want the same SM resources — so it is opt-in: SCDC_OVERLAP_SCORE=1)
+  const bool overlap_score = !uploaded && !dist_host && env_int("SCDC_OVERLAP_SCORE", 0) && o->iterations > B;
+  const int nm = overlap_score ? 2 : 1;
+  cudaStream_t sS = overlap_score ? h->stream_score : s;
+  for (int i = 0; i < nm; ++i) {
+    if (C == 2) CU(h->M1[i].ensure(msz));
+    CU(h->M2[i].ensure(msz));
+  }
   CU(h->counts.ensure((size_t)R * h->ncols + 1));
   CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
   if (uploaded) {
@@ -505,6 +530,20 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     cudaEvent_t* a; cudaEvent_t* b;
     ~SyncGuard() { for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } }
   } guard3{ready, freed};
+  cudaEvent_t m_ready[2] = {nullptr, nullptr}, m_free[2] = {nullptr, nullptr};
+  SyncGuard guard4{m_ready, m_free};
+  bool m_free_set[2] = {false, false};
+  if (overlap_score) {
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&m_ready[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&m_free[i], cudaEventDisableTiming));
+    }
+    // the score stream must not start before earlier work on the compute stream (counter memset)
+    CU(cudaEventRecord(m_ready[0], s));
+    CU(cudaStreamWaitEvent(sS, m_ready[0], 0));
+  }
+  std::vector<cudaEvent_t> evk;  // timing events on the score stream when it is a separate stream
+  EvGuard guard5{evk};
   bool freed_set[2] = {false, false};
   if (pipelined) {
     for (int i = 0; i < 2; ++i) {
@@ -566,19 +605,23 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     }
     const uint8_t* lab2_b = h->lab2[buf].p + in_sb;            // row stride SB bytes
     const uint32_t* bits1_b = (C == 2) ? h->bits1[buf].p + in_sb / 32 : nullptr;  // row stride SBw words
+    const int mb = overlap_score ? (int)((done / B) & 1) : 0;  // group-means buffer of this batch
+    double* M1b = h->M1[mb].p;
+    double* M2b = h->M2[mb].p;
+    if (overlap_score && m_free_set[mb]) CU(cudaStreamWaitEvent(s, m_free[mb], 0));  // K3 of batch b-2 has read it
     CU(mark(evs, s));
     if (C == 2) {
       const int nWC = B / 128, W = 8;
       const long long tasks = (long long)G * nWC;
       scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, T, nWC, h->segptr.p, h->rowidx_s.p,
                                                                            h->values_s.p, bits1_b, SBw, h->ngroup.p,
-                                                                           h->gene_order.p, h->M1.p);
+                                                                           h->gene_order.p, M1b);
       CU(cudaGetLastError());
       ++launches; ++reduce_launches;
     }
-    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, (int)SB, s)
-                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, (int)SB, s)
-                                   : launch_scatter<1>(h, pl, B, lab2_b, (int)SB, s);
+    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, (int)SB, M2b, s)
+                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, (int)SB, M2b, s)
+                                   : launch_scatter<1>(h, pl, B, lab2_b, (int)SB, M2b, s);
     CU(le);
     ++launches; ++reduce_launches;
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
@@ -586,28 +629,33 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     reduce_bytes += (double)C * ((double)h->nnz * (sv + 4.0) + 4.0 * (G + 1)) + (double)B * N * (C == 2 ? 1.125 : 1.0) +
                     (double)C * B * K * G * sv;
     CU(mark(evs, s));
+    if (overlap_score) {
+      CU(cudaEventRecord(m_ready[mb], s));
+      CU(cudaStreamWaitEvent(sS, m_ready[mb], 0));
+      CU(mark(evk, sS));
+    }
     if (R > 0 && !dist_host && !env_int("SCDC_SCORE_V1", 0)) {
       scdc::ScoreV2Args A;
       A.G = G; A.T = T; A.Tp = T | 1; A.K = K; A.nL = h->nL; A.nS = h->nS; A.ncols = h->ncols; A.score_type = o->score_type;
       A.nChunks = (nb + 31) / 32; A.n_valid = nb; A.R = R;
       const int n_arr = (C == 2) ? 8 + h->nS : 2;
       int P = 32;
-      const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", 100) * 1024;
+      const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", overlap_score ? 24 : 100) * 1024;
       while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > smem_target) P >>= 1;
       P = env_int("SCDC_SCORE_P", P);
       A.P = P;
       const size_t smem = (size_t)n_arr * P * A.Tp * 8;
       A.task_lri = h->task_lri.p; A.task_beg = h->task_beg.p; A.task_end = h->task_end.p; A.srow = h->srow.p;
       A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p; A.thr = h->thr.p;
-      A.M1 = h->M1.p; A.M2 = h->M2.p; A.counts = h->counts.p;
+      A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p;
       if (C == 2) {
         auto kern = scdc::k_score_v2<2, kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, h->score_threads, smem, s>>>(A);
+        kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
       } else {
         auto kern = scdc::k_score_v2<1, kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, h->score_threads, smem, s>>>(A);
+        kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
       }
       CU(cudaGetLastError());
       ++launches;
@@ -616,15 +664,21 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       A.R = R; A.G = G; A.T = T; A.C = C; A.nL = h->nL; A.nR = h->nR; A.ncols = h->ncols; A.score_type = o->score_type;
       A.nChunks = (nb + 31) / 32; A.n_valid = nb;
       A.sub_gene = h->sub_gene.p; A.row_lri = h->row_lri.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p;
-      A.obs = h->obs.p; A.M1 = h->M1.p; A.M2 = h->M2.p; A.counts = h->counts.p;
+      A.obs = h->obs.p; A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p;
       A.dist = dist_host ? h->dist.p : nullptr;
       const int blocks = std::max(1, std::min((R + 7) / 8, h->num_sms * 8));
-      scdc::k_score_count<<<blocks, 256, 0, s>>>(A);
+      scdc::k_score_count<<<blocks, 256, 0, sS>>>(A);
       CU(cudaGetLastError());
       ++launches;
       if (dist_host)
         CU(cudaMemcpyAsync(dist_host + (size_t)done * ncols_d * R, h->dist.p, (size_t)nb * ncols_d * R * sizeof(double),
-                           cudaMemcpyDeviceToHost, s));
+                           cudaMemcpyDeviceToHost, sS));
+    }
+    if (overlap_score) {
+      CU(mark(evk, sS));
+      CU(cudaEventRecord(m_free[mb], sS));
+      m_free_set[mb] = true;
+      if (done + B >= o->iterations) CU(cudaStreamWaitEvent(s, m_free[mb], 0));  // the compute stream ends after the last K3
     }
     CU(mark(evs, s));
     if (uploaded || dist_host) CU(cudaStreamSynchronize(s));  // host source / destination buffers are reused per batch
@@ -645,7 +699,13 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       float b = 0, c = 0;
       cudaEventElapsedTime(&b, evs[i], evs[i + 1]);
       cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
-      st->ms_reduce += b; st->ms_score += c;
+      st->ms_reduce += b;
+      if (!overlap_score) st->ms_score += c;
+    }
+    for (size_t i = 0; i + 1 < evk.size(); i += 2) {  // score stream: overlaps the next batch's ms_reduce
+      float c = 0;
+      cudaEventElapsedTime(&c, evk[i], evk[i + 1]);
+      st->ms_score += c;
     }
     for (size_t i = 0; i + 1 < evl.size(); i += 2) {
       float a = 0;
@@ -739,6 +799,7 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
 
 int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* res) {
   if (!res) return fail(SCDC_EINVAL, "result is NULL");
+  PhaseTimer pt;
   int rc = validate_problem(p);
   if (rc) return rc;
   rc = validate_options(p, p->n_conditions, o);
@@ -765,14 +826,17 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   memset(&res->stats, 0, sizeof res->stats);
   if (W == 1) {
     scdc_handle* h = nullptr;
-    rc = scdc_create(p, ids[0], &h);
+    rc = create_impl(p, ids[0], &h, true);
     if (rc) return rc;
+    pt.lap("perm_counts: create");
     scdc_result r1 = *res;
     r1.counts_device = nullptr;
     rc = scdc_run(h, o, &r1);
+    pt.lap("perm_counts: run");
     res->stats = r1.stats;
     res->stats.ms_upload = h->ms_upload;
     scdc_release(h);
+    pt.lap("perm_counts: release");
     res->stats.ms_total = now_ms() - t0;
     return rc;
   }
@@ -789,7 +853,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     for (int r = 0; r < W; ++r) {
       th.emplace_back([&, r]() {
         memset(&sts[r], 0, sizeof(scdc_stats));
-        rcs[r] = scdc_create(p, ids[r], &hs[r]);
+        rcs[r] = create_impl(p, ids[r], &hs[r], true);
         if (rcs[r]) { errs[r] = g_err; return; }
         const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
         os[r].iterations = e - b;

@@ -710,6 +710,36 @@ __global__ void k_group_means(int G, int K, int T, const int* __restrict__ colpt
   for (int k = 0; k < K; ++k) o[k] = o[k] / ngroup[k];
 }
 
+// thr = min{y : sqrt_rn(y) >= o}: (sqrt(x) >= o) == (x >= thr) for every x because sqrt_rn is monotone non-decreasing.
+__device__ __forceinline__ double next_up(double y) {  // y >= 0, finite
+  return __longlong_as_double(__double_as_longlong(y) + 1);
+}
+__device__ __forceinline__ double next_down(double y) {  // y > 0
+  return __longlong_as_double(__double_as_longlong(y) - 1);
+}
+__global__ void k_product_thresholds(size_t n, const double* __restrict__ obs, double* __restrict__ thr) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double o = obs[i];
+  double y;
+  if (isnan(o)) {
+    y = o;                 // x >= NaN is false, like sqrt(x) >= NA
+  } else if (o <= 0.0) {
+    y = 0.0;               // sqrt(x) >= o for every x >= 0; x < 0 gives NaN >= o (false) and x >= 0 false alike
+  } else if (isinf(o)) {
+    y = o;
+  } else {
+    y = o * o;
+    if (isinf(y)) {
+      // sqrt(DBL_MAX) < o: only +inf passes
+    } else {
+      while (y > 0.0 && sqrt(next_down(y)) >= o) y = next_down(y);
+      while (sqrt(y) < o) y = next_up(y);  // may step up to +inf
+    }
+  }
+  thr[i] = y;
+}
+
 __global__ void k_widen_counts(size_t n, const uint32_t* __restrict__ in, long long* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (long long)in[i];
