@@ -638,9 +638,9 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       scdc::ScoreV2Args A;
       A.G = G; A.T = T; A.Tp = T | 1; A.K = K; A.nL = h->nL; A.nS = h->nS; A.ncols = h->ncols; A.score_type = o->score_type;
       A.nChunks = (nb + 31) / 32; A.n_valid = nb; A.R = R;
-      const int n_arr = (C == 2) ? 8 + h->nS : 2;
+      const int n_arr = (C == 2) ? 16 + h->nS : 4;  // RAW tiles double-buffered (2 x 8 | 2 x 2) + D tiles
       int P = 32;
-      const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", overlap_score ? 24 : 100) * 1024;
+      const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", 100) * 1024;
       while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > smem_target) P >>= 1;
       P = env_int("SCDC_SCORE_P", P);
       A.P = P;

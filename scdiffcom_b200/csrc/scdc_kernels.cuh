@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
 // at a time:
 //   stage A: min over the LRI's present ligand subunits per (condition, cell type) and the same for the receptor side
 //            (pmin(na.rm = TRUE), reference R/utils_cci.R:613-653), plus the per-subunit cond2 - cond1 differences, go to
-//            shared memory as [replicate][cell type] tiles (2T * P coalesced reads of the group means per pass);
+//            shared memory as [replicate][cell type] tiles (cp.async double-buffered, one tile ahead);
 //   stage B: every row combines its emitter / receiver entries: score, DE difference, `>=` compares, register counters.
 // No ballots, no atomics, no re-reading of the means per row. The one-sided geometric columns compare the PRODUCT with a
 // host-precomputed threshold thr = min{y : sqrt_rn(y) >= observed}; sqrt_rn is monotone, so
@@ -538,14 +538,34 @@ struct ScoreV2Args {
   uint32_t* counts;
 };
 
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared-memory plan: RAW[2 buffers][NA arrays][P][Tp] + D[nS][P][Tp] (differential only), NA = 8 (array = pass*4 + side*2
+// + cond) or 2 (array = side). RAW tiles are filled by cp.async (LDGSTS) one tile ahead of their use, so the global-memory
+// latency of stage A is hidden behind stage B of the previous tile; the fix-up pass (first-subunit differences, extra
+// subunits of complexes folded in with fmin) works shared-to-shared except for the (rare) extra subunits.
 template <int C, int RPT>
 __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
   extern __shared__ __align__(16) double sm_d[];
   __shared__ int s_gs[8];
+  __shared__ int s_extra;
+  constexpr int NA = (C == 2) ? 8 : 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
   const int T = A.T, Tp = A.Tp, P = A.P, K = A.K, nL = A.nL, nS = A.nS;
   if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
+  if (tid == 0) {
+    int extra = 0;
+    for (int s = 0; s < nS; ++s)
+      if (s != 0 && s != nL && A.sub_gene[l * nS + s] >= 0) extra = 1;
+    s_extra = extra;
+  }
   constexpr int NOB = (C == 2) ? 11 : 1;
   int e_[RPT], r_[RPT], rid[RPT];
   double ob[RPT][NOB], th[RPT][2];
@@ -569,116 +589,108 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
     }
   }
   const int tile = P * Tp;  // doubles per staged array
-  const int nHalf = 32 / P;
-  for (int ch = 0; ch < A.nChunks; ++ch) {
-    for (int hf = 0; hf < nHalf; ++hf) {
-      const int pbase = ch * 32 + hf * P;
-      if (pbase >= A.n_valid) break;
-      __syncthreads();
-      // ---------------- stage A ----------------
-      const int n_items = 2 * T * P;
-      if (C == 1) {
-        for (int item = tid; item < n_items; item += nthr) {
-          const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
-          const int s0 = side ? nL : 0, s1 = side ? nS : nL;
-          const size_t lane_off = (size_t)hf * P + p;
-          double m = A.M2[(((size_t)ch * A.G + s_gs[s0]) * K + ct) * 32 + lane_off];  // LIGAND_1 / RECEPTOR_1: always present
+  double* const Dbase = sm_d + 2 * NA * tile;
+  const int n_tiles = (A.n_valid + P - 1) / P;
+  __syncthreads();
+  const int g_first[2] = {s_gs[0], s_gs[nL]};  // LIGAND_1 / RECEPTOR_1: always present
+  const bool has_extra = s_extra != 0;
+  auto issue = [&](int t) {
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    double* dst0 = sm_d + (size_t)(t & 1) * NA * tile;
+    for (int item = tid; item < NA * T * P; item += nthr) {
+      const int p = item % P, rest = item / P, ct = rest % T, a = rest / T;
+      const int side = (C == 2) ? ((a >> 1) & 1) : a, cond = (C == 2) ? (a & 1) : 0, pass = (C == 2) ? (a >> 2) : 1;
+      const double* M = pass ? A.M2 : A.M1;
+      cp_async_8(dst0 + a * tile + p * Tp + ct,
+                 M + (((size_t)ch * A.G + g_first[side]) * K + cond * T + ct) * 32 + lane0 + p);
+    }
+    cp_async_commit();
+  };
+  if (n_tiles > 0) issue(0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();  // tile t is in shared memory for every thread
+    double* raw = sm_d + (size_t)(t & 1) * NA * tile;
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    if (C == 2 || has_extra) {
+      // ---------------- fix-up: differences of the first subunits, extra subunits folded in ----------------
+      for (int item = tid; item < 2 * T * P; item += nthr) {
+        const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+        const int s0 = side ? nL : 0, s1 = side ? nS : nL;
+        const int o = p * Tp + ct;
+        if (C == 2) {
+          double* b1 = raw + side * 2 * tile + o;  // pass 1: [0] cond1, [tile] cond2 ; pass 2: [4 tile], [5 tile]
+          double m10 = b1[0], m11 = b1[tile], m20 = b1[4 * tile], m21 = b1[5 * tile];
+          Dbase[s0 * tile + o] = m11 - m10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
           for (int s = s0 + 1; s < s1; ++s) {
             const int g = s_gs[s];
-            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane_off]);
-          }
-          sm_d[side * tile + p * Tp + ct] = m;
-        }
-      } else {
-        // two items per iteration, first-subunit loads of both issued before any use (the means are not L2-resident:
-        // memory-level parallelism matters); extra subunits of a complex are rare and handled after
-        for (int item0 = tid; item0 < n_items; item0 += 2 * nthr) {
-          double v10[2], v11[2], v20[2], v21[2];
-          int pp[2], cc[2], sd[2];
-          bool ok[2];
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const int item = item0 + w * nthr;
-            ok[w] = item < n_items;
-            const int it = ok[w] ? item : item0;
-            pp[w] = it % P;
-            const int rest = it / P;
-            cc[w] = rest % T;
-            sd[w] = rest / T;
-            const int g = s_gs[sd[w] ? nL : 0];
-            const size_t i0 = (((size_t)ch * A.G + g) * K + cc[w]) * 32 + (size_t)hf * P + pp[w], i1 = i0 + (size_t)T * 32;
-            v10[w] = A.M1[i0]; v11[w] = A.M1[i1]; v20[w] = A.M2[i0]; v21[w] = A.M2[i1];
-          }
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            if (!ok[w]) continue;
-            const int p = pp[w], ct = cc[w], side = sd[w];
-            const int s0 = side ? nL : 0, s1 = side ? nS : nL;
-            double m10 = v10[w], m11 = v11[w], m20 = v20[w], m21 = v21[w];
-            sm_d[(8 + s0) * tile + p * Tp + ct] = v11[w] - v10[w];  // cond2 - cond1 (reference R/utils_cci.R:212-239)
-            for (int s = s0 + 1; s < s1; ++s) {
-              const int g = s_gs[s];
-              double d = 0.0;
-              if (g >= 0) {
-                const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + (size_t)hf * P + p, i1 = i0 + (size_t)T * 32;
-                const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
-                d = a11 - a10;
-                m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
-              }
-              sm_d[(8 + s) * tile + p * Tp + ct] = d;
+            double d = 0.0;
+            if (g >= 0) {
+              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
+              const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
+              d = a11 - a10;
+              m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
             }
-            double* base = sm_d + side * 2 * tile + p * Tp + ct;  // arrays: pass*4 + side*2 + cond
-            base[0] = m10; base[tile] = m11; base[4 * tile] = m20; base[5 * tile] = m21;
+            Dbase[s * tile + o] = d;
           }
+          if (has_extra) { b1[0] = m10; b1[tile] = m11; b1[4 * tile] = m20; b1[5 * tile] = m21; }
+        } else {
+          double m = raw[side * tile + o];
+          for (int s = s0 + 1; s < s1; ++s) {
+            const int g = s_gs[s];
+            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p]);
+          }
+          raw[side * tile + o] = m;
         }
       }
       __syncthreads();
-      // ---------------- stage B ----------------
-      const int pmax = min(P, A.n_valid - pbase);
+    }
+    // ---------------- stage B ----------------
+    const int pmax = min(P, A.n_valid - pb);
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-        if (rid[q] < 0) continue;
-        const int e = e_[q], r = r_[q];
-        if (C == 1) {
-          const double* pa = sm_d + e;
-          const double* pb = sm_d + tile + r;
-          if (A.score_type == 0) {
+    for (int q = 0; q < RPT; ++q) {
+      if (rid[q] < 0) continue;
+      const int e = e_[q], r = r_[q];
+      if (C == 1) {
+        const double* pa = raw + e;
+        const double* pbp = raw + tile + r;
+        if (A.score_type == 0) {
 #pragma unroll 4
-            for (int p = 0; p < pmax; ++p) cnt[q][0] += (pa[p * Tp] * pb[p * Tp] >= th[q][0]) ? 1u : 0u;
-          } else {
-#pragma unroll 4
-            for (int p = 0; p < pmax; ++p) cnt[q][0] += ((pa[p * Tp] + pb[p * Tp]) / 2 >= ob[q][0]) ? 1u : 0u;
-          }
+          for (int p = 0; p < pmax; ++p) cnt[q][0] += (pa[p * Tp] * pbp[p * Tp] >= th[q][0]) ? 1u : 0u;
         } else {
-          const double aob0 = fabs(ob[q][0]);
+#pragma unroll 4
+          for (int p = 0; p < pmax; ++p) cnt[q][0] += ((pa[p * Tp] + pbp[p * Tp]) / 2 >= ob[q][0]) ? 1u : 0u;
+        }
+      } else {
+        const double aob0 = fabs(ob[q][0]);
 #pragma unroll 2
-          for (int p = 0; p < pmax; ++p) {
-            const double* pa = sm_d + p * Tp + e;            // ligand side arrays 0,1 (pass 1), 4,5 (pass 2)
-            const double* pb = sm_d + 2 * tile + p * Tp + r;  // receptor side arrays 2,3 (pass 1), 6,7 (pass 2)
-            const double a10 = pa[0], a11 = pa[tile], a20 = pa[4 * tile], a21 = pa[5 * tile];
-            const double b10 = pb[0], b11 = pb[tile], b20 = pb[4 * tile], b21 = pb[5 * tile];
-            double de;
-            if (A.score_type == 0) {
-              de = sqrt(a11 * b11) - sqrt(a10 * b10);
-              cnt[q][1] += (a20 * b20 >= th[q][0]) ? 1u : 0u;
-              cnt[q][2] += (a21 * b21 >= th[q][1]) ? 1u : 0u;
-            } else {
-              de = (a11 + b11) / 2 - (a10 + b10) / 2;
-              cnt[q][1] += ((a20 + b20) / 2 >= ob[q][1]) ? 1u : 0u;
-              cnt[q][2] += ((a21 + b21) / 2 >= ob[q][2]) ? 1u : 0u;
-            }
-            cnt[q][0] += (fabs(de) >= aob0) ? 1u : 0u;
+        for (int p = 0; p < pmax; ++p) {
+          const double* pa = raw + p * Tp + e;             // ligand side arrays 0,1 (pass 1), 4,5 (pass 2)
+          const double* pbp = raw + 2 * tile + p * Tp + r;  // receptor side arrays 2,3 (pass 1), 6,7 (pass 2)
+          const double a10 = pa[0], a11 = pa[tile], a20 = pa[4 * tile], a21 = pa[5 * tile];
+          const double b10 = pbp[0], b11 = pbp[tile], b20 = pbp[4 * tile], b21 = pbp[5 * tile];
+          double de;
+          if (A.score_type == 0) {
+            de = sqrt(a11 * b11) - sqrt(a10 * b10);
+            cnt[q][1] += (a20 * b20 >= th[q][0]) ? 1u : 0u;
+            cnt[q][2] += (a21 * b21 >= th[q][1]) ? 1u : 0u;
+          } else {
+            de = (a11 + b11) / 2 - (a10 + b10) / 2;
+            cnt[q][1] += ((a20 + b20) / 2 >= ob[q][1]) ? 1u : 0u;
+            cnt[q][2] += ((a21 + b21) / 2 >= ob[q][2]) ? 1u : 0u;
+          }
+          cnt[q][0] += (fabs(de) >= aob0) ? 1u : 0u;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-              if (s < nS) {
-                const double d = sm_d[(8 + s) * tile + p * Tp + (s < nL ? e : r)];
-                cnt[q][3 + s] += (fabs(d) >= fabs(ob[q][3 + s])) ? 1u : 0u;
-              }
+          for (int s = 0; s < 8; ++s) {
+            if (s < nS) {
+              const double d = Dbase[s * tile + p * Tp + (s < nL ? e : r)];
+              cnt[q][3 + s] += (fabs(d) >= fabs(ob[q][3 + s])) ? 1u : 0u;
             }
           }
         }
       }
     }
+    __syncthreads();  // everyone is done with buffer t & 1 and D before they are overwritten
   }
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
