@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -878,10 +879,26 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   const double t1 = now_ms();
   const size_t n = (size_t)p->n_rows * hs[0]->ncols;
   std::vector<DBuf<long long>> wide(W);
-  std::vector<void*> comms(W, nullptr);
+  // communicators are created once per device set and kept for the life of the process (ncclCommInitAll costs ~1.5 s)
+  static std::mutex comm_mu;
+  static std::vector<int> comm_devs;
+  static std::vector<void*> comm_cache;
+  std::lock_guard<std::mutex> comm_lock(comm_mu);
   std::vector<int> devs(ids.begin(), ids.begin() + W);
-  int nrc = g_nccl.CommInitAll(comms.data(), W, devs.data());
-  if (nrc != 0) { cleanup(); return fail(SCDC_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); }
+  int nrc = 0;
+  if (comm_devs != devs) {
+    for (void* c : comm_cache) if (c) g_nccl.CommDestroy(c);
+    comm_cache.assign(W, nullptr);
+    comm_devs.clear();
+    nrc = g_nccl.CommInitAll(comm_cache.data(), W, devs.data());
+    if (nrc != 0) {
+      comm_cache.clear();
+      cleanup();
+      return fail(SCDC_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+    }
+    comm_devs = devs;
+  }
+  std::vector<void*>& comms = comm_cache;
   int bad = 0;
   for (int r = 0; r < W && !bad; ++r) {
     cudaSetDevice(hs[r]->device);
@@ -906,7 +923,6 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     cudaSetDevice(hs[0]->device);
     if (cudaMemcpy(raw.data(), wide[0].p, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) bad = 3;
   }
-  for (int r = 0; r < W; ++r) if (comms[r]) g_nccl.CommDestroy(comms[r]);
   if (bad) {
     for (auto& w : wide) { w.release(); }
     cleanup();
