@@ -135,7 +135,8 @@ def run_reference(args):
     # each step = a bounded sample; size it from a pilot so that steps + warmup fit in ~2 minutes
     rate, _, _ = cpu_port_rate(prob, target_s=2.0)
     per_step = max(cores, int(rate * min(20.0, 100.0 / max(1, args.steps + args.warmup))))
-    per_step = (per_step // cores) * cores
+    per_step = min(per_step, int(cfg["iterations"]))
+    per_step = max(cores, (per_step // cores) * cores)
     cond, ct = oracle_c.philox_labels(prob, per_step, seed=3)
     for _ in range(args.warmup):
         oracle_c.perm_counts(prob, ct, cond, nthreads=cores)
@@ -259,7 +260,9 @@ def run_ours(args):
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "bytes_per_launch": bytes_reduce / max(1, launches), "ms_per_launch": ms_reduce / max(1, launches),
             "launches": launches,
-            "note": "lane = replicate batching makes the kernel shared-memory-accumulate bound, not HBM bound (DESIGN.md)",
+            "note": "lane = replicate batching makes the kernel shared-memory-pipe bound, not HBM bound (DESIGN.md section 3): "
+                    "ncu l1tex__throughput 98.7 % (profiles/r1_final_config2_raw.csv)",
+            "unbatched_equivalent_gbs": (12.0 * prob.nnz * prob.n_conditions) * (world * iters * args.steps) / (ms_reduce / 1e3) / 1e9 if ms_reduce > 0 else None,
         }
         shares = {k: sum(s[k] for s in stats_acc) for k in ("ms_labels", "ms_reduce", "ms_score", "ms_device")}
         cpu_rate, cores, sample = (None, None, None)
