@@ -153,6 +153,11 @@ int scdc_group_means(scdc_handle* handle, double* means, double* detection_rate)
 int scdc_draw_labels(scdc_handle* handle, uint64_t seed, int64_t perm_offset, int64_t n, uint8_t* cond_out,
                      uint8_t* ct_out);
 
+/* Debug / test hook: checks the DE-column decision procedure of the score kernel (rsqrt.approx band filter + IEEE sqrt
+ * fall-back) against the plain IEEE expression |sqrt(x2) - sqrt(x1)| >= |observed| on n adversarial inputs.
+ * out[0] = mismatches (must be 0), out[1] = decisions taken by the fast path, out[2] = approximations outside 2^-20. */
+int scdc_selftest_de_filter(uint64_t n, uint64_t seed, uint64_t out[3]);
+
 const char* scdc_last_error(void); /* thread-local message of the last failing call on this thread */
 int scdc_device_count(void);       /* visible devices with compute capability 10.x (0 when there is none) */
 const char* scdc_version(void);

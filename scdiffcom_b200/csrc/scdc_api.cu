@@ -106,7 +106,8 @@ struct scdc_handle {
   std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
   // K3 v2: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
-  DBuf<double> thr;
+  DBuf<double> thr, obs_sub;   // obs_sub: [L][T][nS] common observed subunit differences (factorised subunit columns)
+  bool fact_ok = false;
   int n_tasks = 0, score_threads = 256;
   // per-run workspace (grown on demand)
   DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
@@ -357,6 +358,27 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       scdc::k_product_thresholds<<<(unsigned)(((size_t)h->R * C + 255) / 256), 256, 0, s>>>(
           (size_t)h->R * C, h->obs.p + (C == 2 ? (size_t)h->R : 0), h->thr.p);
       CU(cudaGetLastError());
+    }
+    std::vector<double> obs_sub;
+    if (C == 2 && (long long)T * h->nS <= 2 * kScoreThreads) {
+      // The subunit columns of a row depend only on (LRI, emitter) / (LRI, receiver). If the observed subunit
+      // differences agree bitwise across the rows sharing such a pair (true for tables built by the reference, where they
+      // are joins of the same group means), K3 counts them once per (cell type, subunit).
+      const size_t n_tab = (size_t)h->L * T * h->nS;
+      obs_sub.assign(n_tab, std::nan(""));
+      std::vector<uint8_t> seen(n_tab, 0);
+      bool ok = true;
+      for (int r = 0; r < h->R && ok; ++r) {
+        for (int sidx = 0; sidx < h->nS; ++sidx) {
+          const int ctx = (sidx < h->nL) ? p->row_emit[r] : p->row_recv[r];
+          const size_t k = ((size_t)p->row_lri[r] * T + ctx) * h->nS + sidx;
+          const double v = p->observed[(size_t)(3 + sidx) * h->R + r];
+          if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
+          else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
+        }
+      }
+      h->fact_ok = ok && !env_int("SCDC_NO_FACT", 0);
+      if (h->fact_ok) CU(h->obs_sub.upload(obs_sub.data(), n_tab, s));
     }
     CU(h->srow.upload(srow.data(), srow.size(), s));
     CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
@@ -650,9 +672,21 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p; A.thr = h->thr.p;
       A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p;
       if (C == 2) {
-        auto kern = scdc::k_score_v2<2, kScoreRPT>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
+        scdc::ScoreDiffArgs D;
+        D.G = G; D.T = T; D.Tp = A.Tp; D.K = K; D.nL = h->nL; D.nR = h->nR; D.score_type = o->score_type;
+        D.n_valid = nb; D.P = P; D.R = R;
+        D.task_lri = A.task_lri; D.task_beg = A.task_beg; D.task_end = A.task_end; D.srow = A.srow;
+        D.sub_gene = A.sub_gene; D.row_emit = A.row_emit; D.row_recv = A.row_recv; D.obs = A.obs; D.thr = A.thr;
+        D.obs_sub = h->obs_sub.p; D.M1 = M1b; D.M2 = M2b; D.counts = h->counts.p;
+        if (h->fact_ok) {
+          auto kern = scdc::k_score_diff<kScoreRPT, true>;
+          CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
+        } else {
+          auto kern = scdc::k_score_diff<kScoreRPT, false>;
+          CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
+        }
       } else {
         auto kern = scdc::k_score_v2<1, kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -964,6 +998,22 @@ int scdc_group_means(scdc_handle* h, double* means, double* detection_rate) {
     CU(cudaMemcpyAsync(dst, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
+  return SCDC_OK;
+}
+
+int scdc_selftest_de_filter(uint64_t n, uint64_t seed, uint64_t out[3]) {
+  if (!out || n == 0) return fail(SCDC_EINVAL, "out is NULL or n == 0");
+  std::vector<int> ids;
+  if (count_sm100_devices(&ids) == 0) return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x");
+  CU(cudaSetDevice(ids[0]));
+  DBuf<unsigned long long> d;
+  CU(d.alloc(3));
+  CU(cudaMemset(d.p, 0, 3 * sizeof(unsigned long long)));
+  scdc::k_selftest_de<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, d.p);
+  CU(cudaGetLastError());
+  unsigned long long hres[3];
+  CU(cudaMemcpy(hres, d.p, sizeof hres, cudaMemcpyDeviceToHost));
+  out[0] = hres[0]; out[1] = hres[1]; out[2] = hres[2];
   return SCDC_OK;
 }
 

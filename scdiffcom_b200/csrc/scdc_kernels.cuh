@@ -711,6 +711,263 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K3, differential mode (production): same block / tile structure as k_score_v2, tuned for the 3 + nL + nR columns.
+//   * tiles are interleaved [side][replicate][cell type][pass*2 + cond]: a row reads its emitter's four ligand minima
+//     and its receiver's four receptor minima with two 16-byte loads each and no per-access index arithmetic;
+//   * FACT: the per-subunit columns |L_i / R_j cond2 - cond1| >= |observed| depend only on (LRI, emitter) resp.
+//     (LRI, receiver). When the observed subunit differences are bitwise equal across the rows that share that pair
+//     (always true for the reference's tables, checked on the host), they are counted once per (cell type, subunit) and
+//     added to the rows at the end instead of once per row;
+//   * the DE column |sqrt(x2) - sqrt(x1)| >= |observed| is decided from rsqrt.approx when the approximation's error band
+//     cannot change the outcome (the band is 8x the documented 2^-20 relative error) and recomputed with the IEEE sqrt
+//     otherwise, so the decision is always the exact one.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_approx(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+// exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0
+__device__ __forceinline__ bool de_exceeds(double x1, double x0, double aob) {
+  const double s1 = (x1 == 0.0) ? 0.0 : x1 * rsqrt_approx(x1);
+  const double s0 = (x0 == 0.0) ? 0.0 : x0 * rsqrt_approx(x0);
+  const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;  // 2^-17
+  // products far outside [1e-280, 1e280] (flush-to-zero / overflow of the approximation), NaN or negative: exact path
+  const bool in_range = (x1 == 0.0 || (x1 > 1e-280 && x1 < 1e280)) && (x0 == 0.0 || (x0 > 1e-280 && x0 < 1e280));
+  if (in_range && d - slack > aob) return true;
+  if (in_range && d + slack < aob) return false;
+  return fabs(sqrt(x1) - sqrt(x0)) >= aob;
+}
+
+// Self-test of de_exceeds against the plain IEEE expression on adversarial inputs (thresholds within a few ulps of the
+// true difference, exact ties, zeros, tiny / huge products). out[0] = mismatches, out[1] = decisions taken by the fast path.
+__global__ void k_selftest_de(unsigned long long n, unsigned long long seed, unsigned long long* out) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[4];
+  philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x5eedu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const int kind = w[3] & 15;
+  // log-uniform magnitudes; kind selects the exponent range
+  const double span = (kind < 10) ? 12.0 : (kind < 13 ? 300.0 : 40.0);
+  double x0 = exp2((w[0] * (1.0 / 4294967296.0) - 0.5) * span), x1 = exp2((w[1] * (1.0 / 4294967296.0) - 0.5) * span);
+  if (kind == 10) x0 = 0.0;
+  if (kind == 11) x1 = x0;
+  if (kind == 12) { x0 = 0.0; x1 = 0.0; }
+  const double truth = fabs(sqrt(x1) - sqrt(x0));
+  // threshold: the exact difference moved by -3..+3 ulps, or scaled by 1 +- 2^-k, or unrelated
+  double aob = truth;
+  const int mode = (w[2] >> 4) & 7, amt = (int)(w[2] & 7) - 3;
+  if (mode < 3) aob = __longlong_as_double(__double_as_longlong(truth) + amt);
+  else if (mode < 6) aob = truth * (1.0 + (amt >= 0 ? 1.0 : -1.0) * exp2(-(double)(10 + 6 * (w[2] >> 8 & 7))));
+  else aob = exp2((w[2] * (1.0 / 4294967296.0) - 0.5) * span * 0.5);
+  if (!(aob >= 0.0)) aob = 0.0;
+  const bool want = truth >= aob;
+  const bool got = de_exceeds(x1, x0, aob);
+  if (want != got) atomicAdd(&out[0], 1ull);
+  // was it decidable without the IEEE sqrt?
+  const double s1 = (x1 == 0.0) ? 0.0 : x1 * rsqrt_approx(x1), s0 = (x0 == 0.0) ? 0.0 : x0 * rsqrt_approx(x0);
+  const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;
+  if (d - slack > aob || d + slack < aob) atomicAdd(&out[1], 1ull);
+  // the approximation itself must stay well inside the band used by the filter
+  if (x1 > 1e-280 && x1 < 1e280 && fabs(s1 - sqrt(x1)) > sqrt(x1) * 9.5367431640625e-07) atomicAdd(&out[2], 1ull);  // 2^-20
+}
+
+struct ScoreDiffArgs {
+  int G, T, Tp, K, nL, nR, score_type;
+  int n_valid, P;
+  int R;
+  const int* task_lri;
+  const int* task_beg;
+  const int* task_end;
+  const int* srow;
+  const int* sub_gene;
+  const int* row_emit;
+  const int* row_recv;
+  const double* obs;      // column-major [R][ncols], original row ids
+  const double* thr;      // column-major [R][2]
+  const double* obs_sub;  // FACT: [L][T][nS] common observed subunit differences (NaN = unused / absent)
+  const double* M1;
+  const double* M2;
+  uint32_t* counts;
+};
+
+template <int RPT, bool FACT>
+__global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
+  extern __shared__ __align__(16) double sm_d[];
+  __shared__ int s_gs[8];
+  __shared__ int s_extra;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
+  const int T = A.T, Tp = A.Tp, P = A.P, K = A.K, nL = A.nL, nR = A.nR, nS = nL + nR;
+  const int ncols = 3 + nS;
+  if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
+  if (tid == 0) {
+    int extra = 0;
+    for (int s = 0; s < nS; ++s)
+      if (s != 0 && s != nL && A.sub_gene[l * nS + s] >= 0) extra = 1;
+    s_extra = extra;
+  }
+  constexpr int NOB = FACT ? 3 : 11;
+  int e_[RPT], r_[RPT], rid[RPT];
+  double ob[RPT][NOB], th[RPT][2];
+  uint32_t cnt[RPT][NOB];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int pos = rb + tid + q * nthr;
+    rid[q] = (pos < re) ? A.srow[pos] : -1;
+    e_[q] = r_[q] = 0;
+#pragma unroll
+    for (int c = 0; c < NOB; ++c) { ob[q][c] = 0.0; cnt[q][c] = 0; }
+    th[q][0] = th[q][1] = 0.0;
+    if (rid[q] >= 0) {
+      e_[q] = A.row_emit[rid[q]];
+      r_[q] = A.row_recv[rid[q]];
+#pragma unroll
+      for (int c = 0; c < NOB; ++c)
+        if (c < ncols) ob[q][c] = A.obs[(size_t)c * A.R + rid[q]];
+      th[q][0] = A.thr[rid[q]];
+      th[q][1] = A.thr[(size_t)A.R + rid[q]];
+    }
+  }
+  // FACT: (cell type, subunit) pairs owned by this thread for the whole launch: items tid and tid + nthr of T * nS
+  double so[2] = {0.0, 0.0};
+  uint32_t sc[2] = {0, 0};
+  if (FACT) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int item = tid + w * nthr;
+      so[w] = (item < T * nS) ? fabs(A.obs_sub[(size_t)l * T * nS + item]) : __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+  const int sideStride = P * Tp * 4;            // doubles per side inside one RAW buffer
+  const int rawSize = 2 * sideStride;           // doubles per RAW buffer
+  double* const DL = sm_d + 2 * rawSize;        // [P][Tp][nL]
+  double* const DR = DL + P * Tp * nL;          // [P][Tp][nR]
+  const int n_tiles = (A.n_valid + P - 1) / P;
+  __syncthreads();
+  const int g_first[2] = {s_gs[0], s_gs[nL]};
+  const bool has_extra = s_extra != 0;
+  auto issue = [&](int t) {
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    double* dst0 = sm_d + (size_t)(t & 1) * rawSize;
+    for (int item = tid; item < 8 * T * P; item += nthr) {
+      const int p = item % P, rest = item / P, ct = rest % T, rest2 = rest / T, k = rest2 & 3, side = rest2 >> 2;
+      const double* M = (k >> 1) ? A.M2 : A.M1;
+      cp_async_8(dst0 + side * sideStride + (p * Tp + ct) * 4 + k,
+                 M + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T + ct) * 32 + lane0 + p);
+    }
+    cp_async_commit();
+  };
+  if (n_tiles > 0) issue(0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    double* raw = sm_d + (size_t)(t & 1) * rawSize;
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    // ---------------- fix-up: first-subunit differences, extra subunits of complexes folded in ----------------
+    for (int item = tid; item < 2 * T * P; item += nthr) {
+      const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+      const int s0 = side ? nL : 0, nSide = side ? nR : nL;
+      double* b4 = raw + side * sideStride + (p * Tp + ct) * 4;  // {pass1 c1, pass1 c2, pass2 c1, pass2 c2}
+      double* dd = (side ? DR : DL) + (p * Tp + ct) * nSide;
+      double m10 = b4[0], m11 = b4[1], m20 = b4[2], m21 = b4[3];
+      dd[0] = m11 - m10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
+      for (int k = 1; k < nSide; ++k) {
+        const int g = s_gs[s0 + k];
+        double d = 0.0;
+        if (g >= 0) {
+          const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
+          const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
+          d = a11 - a10;
+          m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
+        }
+        dd[k] = d;
+      }
+      if (has_extra) { b4[0] = m10; b4[1] = m11; b4[2] = m20; b4[3] = m21; }
+    }
+    __syncthreads();
+    const int pmax = min(P, A.n_valid - pb);
+    // ---------------- subunit columns, once per (cell type, subunit) ----------------
+    if (FACT) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int item = tid + w * nthr;
+        if (item < T * nS) {
+          const int ct = item / nS, s = item % nS;
+          const int nSide = (s < nL) ? nL : nR;
+          const double* pd = ((s < nL) ? DL : DR) + ct * nSide + ((s < nL) ? s : s - nL);
+          const int stride = Tp * nSide;
+          uint32_t c = 0;
+          for (int p = 0; p < pmax; ++p) c += (fabs(pd[p * stride]) >= so[w]) ? 1u : 0u;
+          sc[w] += c;
+        }
+      }
+    }
+    // ---------------- stage B: rows ----------------
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if (rid[q] < 0) continue;
+      const double2* pa = reinterpret_cast<const double2*>(raw + e_[q] * 4);
+      const double2* pbp = reinterpret_cast<const double2*>(raw + sideStride + r_[q] * 4);
+      const double aob0 = fabs(ob[q][0]);
+      const int st2 = Tp * 2;  // double2 per replicate
+      uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 2
+      for (int p = 0; p < pmax; ++p) {
+        const double2 a1 = pa[p * st2], a2 = pa[p * st2 + 1];
+        const double2 b1 = pbp[p * st2], b2 = pbp[p * st2 + 1];
+        if (A.score_type == 0) {
+          c0 += de_exceeds(a1.y * b1.y, a1.x * b1.x, aob0) ? 1u : 0u;
+          c1 += (a2.x * b2.x >= th[q][0]) ? 1u : 0u;
+          c2 += (a2.y * b2.y >= th[q][1]) ? 1u : 0u;
+        } else {
+          const double de = (a1.y + b1.y) / 2 - (a1.x + b1.x) / 2;
+          c0 += (fabs(de) >= aob0) ? 1u : 0u;
+          c1 += ((a2.x + b2.x) / 2 >= ob[q][1]) ? 1u : 0u;
+          c2 += ((a2.y + b2.y) / 2 >= ob[q][2]) ? 1u : 0u;
+        }
+        if (!FACT) {
+          const double* dl = DL + (p * Tp + e_[q]) * nL;
+          const double* dr = DR + (p * Tp + r_[q]) * nR;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < nS) {
+              const double d = (s < nL) ? dl[s] : dr[s - nL];
+              cnt[q][FACT ? 0 : 3 + s] += (fabs(d) >= fabs(ob[q][FACT ? 0 : 3 + s])) ? 1u : 0u;
+            }
+          }
+        }
+      }
+      cnt[q][0] += c0; cnt[q][1] += c1; cnt[q][2] += c2;
+    }
+    __syncthreads();  // everyone is done with RAW buffer t & 1 and the D tiles before they are overwritten
+  }
+  uint32_t* s_sub = reinterpret_cast<uint32_t*>(sm_d);  // [T][nS], reuses the tile memory
+  if (FACT) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int item = tid + w * nthr;
+      if (item < T * nS) s_sub[item] = sc[w];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rid[q] < 0) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < nS) {
+        const uint32_t add = FACT ? s_sub[((s < nL) ? e_[q] : r_[q]) * nS + s] : cnt[q][FACT ? 0 : 3 + s];
+        A.counts[(size_t)(3 + s) * A.R + rid[q]] += add;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Observed-pass helper (aggregate_cells on the original labels): one thread per gene, sequential over the column.
 // out is column-major [K][G]: out[g*K + k]. mode 0: sum of x ; mode 1: sum of 1*(x > 0).
 // ------------------------------------------------------------------------------------------------------------------

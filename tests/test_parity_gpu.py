@@ -192,3 +192,16 @@ def test_in_library_multi_gpu_equals_single_gpu(liver_cases):
         a = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=1)["counts"]
         b = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=2)["counts"]
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_de_column_filter_is_exact():
+    """The DE column is decided from rsqrt.approx when its error band cannot change the outcome and from the IEEE sqrt
+    otherwise: 50 M adversarial (x1, x0, |observed|) triples, thresholds within ulps of the true difference included."""
+    import ctypes as C
+    lib = _lib.load()
+    out = (C.c_uint64 * 3)()
+    _lib.check(lib.scdc_selftest_de_filter(50_000_000, 12345, out))
+    mismatches, fast, bad_approx = int(out[0]), int(out[1]), int(out[2])
+    assert mismatches == 0
+    assert bad_approx == 0
+    assert fast > 10_000_000          # the fast path decides whenever the threshold is not within the band
