@@ -456,10 +456,10 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
   return pl;
 }
 
-template <int J>
-cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                           double* M2, cudaStream_t s) {
-  auto kern = scdc::k_scatter<J, 8>;
+template <int J, int U>
+cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
+                             double* M2, cudaStream_t s) {
+  auto kern = scdc::k_scatter<J, U>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
@@ -467,6 +467,16 @@ cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad
   kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
                                         h->ngroup.p, h->gene_order.p, M2);
   return cudaGetLastError();
+}
+
+template <int J>
+cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
+                           double* M2, cudaStream_t s) {
+  // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
+  const int warps_per_sm = pl.blocks_per_sm * pl.W;
+  const int U = env_int("SCDC_U", (J == 1 && warps_per_sm <= 8) ? 16 : 8);
+  if (J == 1 && U == 16) return launch_scatter_u<J, 16>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  return launch_scatter_u<J, 8>(h, pl, Bpad, lab2, lab_stride, M2, s);
 }
 
 int pick_batch(const scdc_handle* h, const scdc_options* o) {

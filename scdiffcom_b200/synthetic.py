@@ -19,6 +19,8 @@ CONFIGS = {
     "config2": dict(n_cells=20_000, n_genes=2500, n_celltypes=15, n_conditions=1, n_lri=5000, iterations=10_000, seed=20261021),
     "config3": dict(n_cells=50_000, n_genes=2500, n_celltypes=25, n_conditions=2, n_lri=5000, iterations=10_000, seed=20261022),
     "config4": dict(n_cells=100_000, n_genes=1854, n_celltypes=30, n_conditions=2, n_lri=4785, iterations=50_000, seed=20261023),
+    # scaled-down stand-in for config 5 (same T = 60, K = 120 kernel regime) for quick tuning runs
+    "config5s": dict(n_cells=60_000, n_genes=400, n_celltypes=60, n_conditions=2, n_lri=800, iterations=4096, seed=20261025),
     "config5": dict(n_cells=250_000, n_genes=2500, n_celltypes=60, n_conditions=2, n_lri=5000, iterations=100_000, seed=20261024),
 }
 
