@@ -222,7 +222,8 @@ def run_ours(args):
 
     # ---- e2e: one-shot C-ABI call with host buffers (H2D + D2H inside the timed region) ----
     e2e_steps = max(1, min(args.steps, 3))
-    perm_counts(prob, iters, seed=seed, perm_offset=rank * iters, device_base=local, batch_size=args.batch)   # warm-up
+    for _ in range(max(3, args.warmup)):   # warm-up (the first cudaMalloc / cudaFree cycles of new sizes are slow)
+        perm_counts(prob, iters, seed=seed, perm_offset=rank * iters, device_base=local, batch_size=args.batch)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

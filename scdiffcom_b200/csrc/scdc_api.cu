@@ -115,9 +115,20 @@ struct scdc_handle {
   DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
   DBuf<int> flag;
   double ms_upload = 0;
+  size_t mem_total = 0;
+  // labels of super-batch 0 drawn ahead of scdc_run (one-shot path: K1 overlaps the H2D of the matrix)
+  struct Pre {
+    bool valid = false;
+    uint64_t seed = 0;
+    int64_t perm_offset = 0, SB = 0;
+    int J = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+  } pre;
 };
 
 namespace {
+
+int prelaunch_labels(scdc_handle* h, const scdc_options* o);
 
 int count_sm100_devices(std::vector<int>* ids) {
   int n = 0;
@@ -136,7 +147,22 @@ int count_sm100_devices(std::vector<int>* ids) {
   return found;
 }
 
-int validate_problem(const scdc_problem* p) {
+// O(nnz) part of the validation: cell indices in range and strictly ascending inside every gene column
+int validate_matrix(const scdc_problem* p) {
+  const int N = p->n_cells, G = p->n_genes;
+  for (int g = 0; g < G; ++g) {
+    for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) {
+      int c = p->rowidx[e];
+      if (c < 0 || c >= N) return fail(SCDC_EINVAL, "rowidx out of range at entry %d", e);
+      if (e > p->colptr[g] && c <= p->rowidx[e - 1])
+        return fail(SCDC_EINVAL, "rowidx not strictly ascending inside gene column %d", g);
+    }
+  }
+  return SCDC_OK;
+}
+
+// everything except the matrix entries (dimensions, labels, LRI table, rows): O(N + G + L + R)
+int validate_meta(const scdc_problem* p) {
   if (!p) return fail(SCDC_EINVAL, "problem is NULL");
   if (p->n_cells < 1 || p->n_genes < 1 || p->n_celltypes < 1 || p->n_lri < 1 || p->n_rows < 0)
     return fail(SCDC_EINVAL, "non-positive dimension (N=%d G=%d T=%d L=%d R=%d)", p->n_cells, p->n_genes,
@@ -152,15 +178,9 @@ int validate_problem(const scdc_problem* p) {
   if (p->n_conditions == 2 && !p->cond_code) return fail(SCDC_EINVAL, "cond_code is NULL in differential mode");
   const int N = p->n_cells, G = p->n_genes, T = p->n_celltypes, C = p->n_conditions;
   if (p->colptr[0] != 0) return fail(SCDC_EINVAL, "colptr[0] != 0");
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < G; ++g)
     if (p->colptr[g + 1] < p->colptr[g]) return fail(SCDC_EINVAL, "colptr not non-decreasing at gene %d", g);
-    for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) {
-      int c = p->rowidx[e];
-      if (c < 0 || c >= N) return fail(SCDC_EINVAL, "rowidx out of range at entry %d", e);
-      if (e > p->colptr[g] && c <= p->rowidx[e - 1])
-        return fail(SCDC_EINVAL, "rowidx not strictly ascending inside gene column %d", g);
-    }
-  }
+  if ((long long)p->colptr[G] > 2147483647LL - 256) return fail(SCDC_EINVAL, "too many non-zeros for 32-bit entry indices");
   std::vector<int64_t> ng((size_t)C * T, 0);
   for (int i = 0; i < N; ++i) {
     int t = p->ct_code[i];
@@ -188,6 +208,11 @@ int validate_problem(const scdc_problem* p) {
       return fail(SCDC_EINVAL, "row %d: LRI %d lacks LIGAND_1 or RECEPTOR_1", r, l);
   }
   return SCDC_OK;
+}
+
+int validate_problem(const scdc_problem* p) {
+  int rc = validate_meta(p);
+  return rc ? rc : validate_matrix(p);
 }
 
 int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* o) {
@@ -220,16 +245,28 @@ void scdc_release(scdc_handle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_labels) cudaStreamDestroy(h->stream_labels);
   if (h->stream_score) cudaStreamDestroy(h->stream_score);
+  if (h->pre.t0) cudaEventDestroy(h->pre.t0);
+  if (h->pre.t1) cudaEventDestroy(h->pre.t1);
   delete h;
 }
 
-static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, bool validated) {
+// o_hint != NULL (one-shot path): the options of the run that follows. The cheap part of the validation has been done by
+// the caller; the O(nnz) matrix check runs on a helper thread and K1 is launched ahead, both overlapping the H2D copies.
+static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, const scdc_options* o_hint) {
   if (!out) return fail(SCDC_EINVAL, "out is NULL");
   *out = nullptr;
   PhaseTimer pt;
-  int rc = validated ? SCDC_OK : validate_problem(p);
+  int rc = o_hint ? SCDC_OK : validate_problem(p);
   if (rc) return rc;
   pt.lap("create: validate");
+  int matrix_rc = SCDC_OK;
+  std::string matrix_err;
+  std::thread matrix_check;
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{matrix_check};
+  if (o_hint) matrix_check = std::thread([&]() { matrix_rc = validate_matrix(p); if (matrix_rc) matrix_err = g_err; });
   std::vector<int> ids;
   if (count_sm100_devices(&ids) == 0)
     return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
@@ -257,6 +294,11 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
   h->num_sms = v;
   CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   h->smem_optin = (size_t)v;
+  {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    h->mem_total = total_b;
+  }
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K;
   cudaStream_t s = h->stream;
   try {
@@ -288,14 +330,26 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       CU(h->ct_seg.upload(ct_seg.data(), ct_seg.size(), s));
     }
     CU(h->colptr.upload(p->colptr, (size_t)G + 1, s));
-    pt.lap("create: context + small prep");
-    CU(h->rowidx.upload(p->rowidx, h->nnz, s));
-    CU(h->values.upload(p->values, h->nnz, s));
     CU(h->ct.upload(ct8.data(), N, s));
     CU(h->cond.upload(cond8.data(), N, s));
     CU(h->ngroup.upload(ngd.data(), K, s));
     CU(h->expect.upload(ng.data(), K, s));
     CU(h->gene_order.upload(order.data(), G, s));
+    pt.lap("create: context + small prep");
+    if (o_hint) {  // K1 needs only the labels: draw the first super-batch while the matrix is copied
+      rc = prelaunch_labels(h.get(), o_hint);
+      if (rc) return rc;
+    }
+    CU(h->rowidx.upload(p->rowidx, h->nnz, s));
+    CU(h->values.upload(p->values, h->nnz, s));
+    if (matrix_check.joinable()) {
+      matrix_check.join();
+      if (matrix_rc) {
+        cudaDeviceSynchronize();
+        g_err = matrix_err;
+        return matrix_rc;
+      }
+    }
     CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
     CU(h->row_lri.upload(p->row_lri, h->R, s));
     CU(h->row_emit.upload(p->row_emit, h->R, s));
@@ -339,7 +393,8 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       for (int l = 0; l < h->L; ++l) start[(size_t)l + 1] += start[l];
       for (int r = 0; r < h->R; ++r) srow[start[p->row_lri[r]]++] = r;
     }
-    h->score_threads = kScoreThreads;  // (64/128-thread blocks were measured slower on configs 2 and 3)
+    h->score_threads = env_int("SCDC_SCORE_THREADS", kScoreThreads);
+    if (h->score_threads < 32 || h->score_threads > kScoreThreads || (h->score_threads & 31)) h->score_threads = kScoreThreads;
     const int rpb = h->score_threads * kScoreRPT;
     for (int b = 0; b < h->R;) {
       int e = b;
@@ -396,7 +451,7 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
   return SCDC_OK;
 }
 
-int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) { return create_impl(p, device, out, false); }
+int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) { return create_impl(p, device, out, nullptr); }
 
 }  // extern "C"
 
@@ -480,18 +535,50 @@ cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad
 }
 
 int pick_batch(const scdc_handle* h, const scdc_options* o) {
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
   const double per_perm = (double)h->C * h->G * h->K * 8.0 + (double)h->N * 1.125 +
                           ((o->perm_ct != nullptr) ? 2.0 * h->N : 0.0) +
                           (o->return_distributions ? (double)h->R * ((h->C == 2) ? 3 : 1) * 8.0 : 0.0);
-  double budget = std::min((double)free_b * 0.5, 24.0e9);
+  double budget = std::min((double)h->mem_total * 0.25, 24.0e9);
   long long B = (long long)(budget / per_perm);
   B = std::min<long long>(B, 4096);
   if (o->batch_size > 0) B = o->batch_size;
   B = std::min<long long>(B, ((o->iterations + 127) / 128) * 128);
   B = std::max<long long>(128, (B / 128) * 128);
   return (int)B;
+}
+
+// replicates per label super-batch (device-drawn labels): as many as the label memory cap allows, normally all
+int64_t pick_super_batch(const scdc_handle* h, const scdc_options* o, int B) {
+  const int64_t iters_pad = ((o->iterations + B - 1) / B) * B;
+  const double per_rep = (double)h->N * (h->C == 2 ? 1.125 : 1.0);
+  const double cap = std::min((double)h->mem_total * 0.1, 8.0e9);
+  int64_t SB = std::max<int64_t>(B, ((int64_t)(cap / per_rep) / B) * B);
+  SB = std::min<int64_t>(SB, iters_pad);
+  const int sb_env = env_int("SCDC_SUPER_BATCH", 0);
+  if (sb_env > 0) SB = std::min<int64_t>(iters_pad, std::max<int64_t>(B, ((int64_t)sb_env / B) * B));
+  return SB;
+}
+
+// One-shot path: draw the labels of super-batch 0 on the label stream right after the small uploads, so that K1 (which
+// needs only the cell labels) overlaps the H2D of the expression matrix. run_device picks them up if the plan matches.
+int prelaunch_labels(scdc_handle* h, const scdc_options* o) {
+  if (o->perm_ct != nullptr || env_int("SCDC_NO_PRELAUNCH", 0)) return SCDC_OK;
+  const int B = pick_batch(h, o);
+  const ScatterPlan pl = plan_scatter(h, B);
+  const int64_t SB = pick_super_batch(h, o, B);
+  CU(h->lab2[0].ensure((size_t)h->N * SB));
+  if (h->C == 2) CU(h->bits1[0].ensure((size_t)h->N * (SB / 32)));
+  if (!h->pre.t0) { CU(cudaEventCreate(&h->pre.t0)); CU(cudaEventCreate(&h->pre.t1)); }
+  cudaEvent_t dep;
+  CU(cudaEventCreateWithFlags(&dep, cudaEventDisableTiming));
+  cudaError_t e1 = cudaEventRecord(dep, h->stream), e2 = cudaStreamWaitEvent(h->stream_labels, dep, 0);
+  cudaEventDestroy(dep);
+  CU(e1); CU(e2);
+  CU(cudaEventRecord(h->pre.t0, h->stream_labels));
+  CU(launch_draw(h, h->stream_labels, o->seed, o->perm_offset, (int)SB, pl.J, h->bits1[0].p, h->lab2[0].p, nullptr, nullptr));
+  CU(cudaEventRecord(h->pre.t1, h->stream_labels));
+  h->pre.valid = true; h->pre.seed = o->seed; h->pre.perm_offset = o->perm_offset; h->pre.SB = SB; h->pre.J = pl.J;
+  return SCDC_OK;
 }
 
 // Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
@@ -508,17 +595,10 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   // allows — normally all of them) in one launch; the reduction then walks it in batches of B. With several
   // super-batches the label buffers are double-buffered and K1 runs one super-batch ahead on a second stream.
   const int64_t iters_pad = ((o->iterations + B - 1) / B) * B;
-  int64_t SB = B;
-  if (!uploaded) {
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    const double per_rep = (double)N * (C == 2 ? 1.125 : 1.0);
-    const double cap = std::min((double)free_b * 0.2, 8.0e9);
-    SB = std::max<int64_t>(B, ((int64_t)(cap / per_rep) / B) * B);
-    SB = std::min<int64_t>(SB, iters_pad);
-    const int sb_env = env_int("SCDC_SUPER_BATCH", 0);
-    if (sb_env > 0) SB = std::min<int64_t>(iters_pad, std::max<int64_t>(B, ((int64_t)sb_env / B) * B));
-  }
+  const int64_t SB = uploaded ? B : pick_super_batch(h, o, B);
+  const bool pre_ok = !uploaded && h->pre.valid && h->pre.seed == o->seed && h->pre.perm_offset == o->perm_offset &&
+                      h->pre.SB == SB && h->pre.J == pl.J;
+  h->pre.valid = false;  // consumed (or stale)
   const int SBw = (int)(SB / 32);
   const bool pipelined = !uploaded && SB < iters_pad;
   const int nbuf = pipelined ? 2 : 1;
@@ -604,8 +684,10 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     cudaError_t e1 = cudaEventRecord(start, s), e2 = cudaStreamWaitEvent(sL, start, 0);
     cudaEventDestroy(start);
     CU(e1); CU(e2);
-    int rc = issue_labels(0, 0);
-    if (rc) return rc;
+    if (!pre_ok) {
+      int rc = issue_labels(0, 0);
+      if (rc) return rc;
+    }
   }
   for (int64_t done = 0; done < o->iterations; done += B) {
     const int nb = (int)std::min<int64_t>(B, o->iterations - done);
@@ -625,7 +707,13 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(mark(evl, s));
       launches += 2;
     } else if (in_sb == 0) {
-      if (!pipelined) {
+      if (pre_ok && done == 0) {
+        CU(cudaStreamWaitEvent(s, h->pre.t1, 0));  // super-batch 0 was drawn ahead by prelaunch_labels (buffer 0)
+        if (pipelined && SB < o->iterations) {
+          int rc = issue_labels(SB, 1);
+          if (rc) return rc;
+        }
+      } else if (!pipelined) {
         int rc = issue_labels(done, 0);
         if (rc) return rc;
       } else {
@@ -752,6 +840,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       cudaEventElapsedTime(&c, evk[i], evk[i + 1]);
       st->ms_score += c;
     }
+    if (pre_ok) {
+      float a = 0;
+      cudaEventElapsedTime(&a, h->pre.t0, h->pre.t1);
+      st->ms_labels += a;  // drawn during scdc_create, overlapped with the matrix upload
+    }
     for (size_t i = 0; i + 1 < evl.size(); i += 2) {
       float a = 0;
       cudaEventElapsedTime(&a, evl[i], evl[i + 1]);
@@ -845,7 +938,7 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
 int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* res) {
   if (!res) return fail(SCDC_EINVAL, "result is NULL");
   PhaseTimer pt;
-  int rc = validate_problem(p);
+  int rc = validate_meta(p);  // the O(nnz) matrix check overlaps the upload (create_impl)
   if (rc) return rc;
   rc = validate_options(p, p->n_conditions, o);
   if (rc) return rc;
@@ -854,8 +947,11 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     return fail(SCDC_EINVAL, "return_distributions set but result.distributions is NULL");
   std::vector<int> ids;
   const int avail = count_sm100_devices(&ids);
-  if (avail == 0)
+  if (avail == 0) {
+    rc = validate_matrix(p);  // argument errors are reported before the missing device
+    if (rc) return rc;
     return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
+  }
   if (o->n_gpus < 0) return fail(SCDC_EINVAL, "n_gpus must be >= 0");
   if (o->device_base < 0 || o->device_base >= avail)
     return fail(SCDC_ENOGPU, "device_base = %d but %d compute-capability-10.x devices are visible", o->device_base, avail);
@@ -871,7 +967,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   memset(&res->stats, 0, sizeof res->stats);
   if (W == 1) {
     scdc_handle* h = nullptr;
-    rc = create_impl(p, ids[0], &h, true);
+    rc = create_impl(p, ids[0], &h, o);
     if (rc) return rc;
     pt.lap("perm_counts: create");
     scdc_result r1 = *res;
@@ -898,13 +994,13 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     for (int r = 0; r < W; ++r) {
       th.emplace_back([&, r]() {
         memset(&sts[r], 0, sizeof(scdc_stats));
-        rcs[r] = create_impl(p, ids[r], &hs[r], true);
-        if (rcs[r]) { errs[r] = g_err; return; }
         const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
         os[r].iterations = e - b;
         os[r].perm_offset = o->perm_offset + b;
         if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
         if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
+        rcs[r] = create_impl(p, ids[r], &hs[r], os[r].iterations > 0 ? &os[r] : nullptr);
+        if (rcs[r]) { errs[r] = g_err; return; }
         if (os[r].iterations > 0) {
           rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
           if (rcs[r]) errs[r] = g_err;

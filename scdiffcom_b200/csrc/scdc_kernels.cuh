@@ -345,14 +345,15 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   const int beg = colptr[g], end = colptr[g + 1];
   const int nst = (end - beg + 31) >> 5;
   const uint8_t* labbase = lab2 + (size_t)cJ * 32 * J + lane * J;
+  // Matrix entries and the flushed means are streamed (evict-first) so that they do not push the labels out of L2.
   // The labels of the NEXT group of U entries are loaded (L2 latency) while the CURRENT group is accumulated, and the
   // entries two stages ahead are in flight from global memory: the read-modify-write chain never waits on a load.
   int cell_n = 0;
   double v_n = 0.0;
-  if (beg + lane < end) { cell_n = rowidx[beg + lane]; v_n = values[beg + lane]; }
+  if (beg + lane < end) { cell_n = __ldcs(rowidx + beg + lane); v_n = __ldcs(values + beg + lane); }
   stage[lane] = pack_entry(cell_n, v_n);
   cell_n = 0; v_n = 0.0;  // padding entries add +0.0 to cell 0's group: bit-neutral
-  if (beg + 32 + lane < end) { cell_n = rowidx[beg + 32 + lane]; v_n = values[beg + 32 + lane]; }
+  if (beg + 32 + lane < end) { cell_n = __ldcs(rowidx + beg + 32 + lane); v_n = __ldcs(values + beg + 32 + lane); }
   __syncwarp();
   double valN[U];
   lab_t lbN[U];
@@ -370,7 +371,7 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
     {
       const int e = beg + (s + 2) * 32 + lane;
       cell_n = 0; v_n = 0.0;
-      if (e < end) { cell_n = rowidx[e]; v_n = values[e]; }
+      if (e < end) { cell_n = __ldcs(rowidx + e); v_n = __ldcs(values + e); }
     }
     __syncwarp();
 #pragma unroll
@@ -401,7 +402,7 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
     const double nk = ngroup[k];
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      M2[(((size_t)(cJ * J + j) * G + g) * K + k) * 32 + lane] = acc[(k * J + j) * 32] / nk;
+      __stcs(&M2[(((size_t)(cJ * J + j) * G + g) * K + k) * 32 + lane], acc[(k * J + j) * 32] / nk);
   }
 }
 
