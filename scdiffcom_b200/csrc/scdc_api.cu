@@ -365,21 +365,34 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       segptr.resize((size_t)G * (T + 1));
       rows_s.resize(h->nnz);
       vals_s.resize(h->nnz);
-      std::vector<int> cnt(T + 1);
-      for (int g = 0; g < G; ++g) {
-        const int b = p->colptr[g], e = p->colptr[g + 1];
-        std::fill(cnt.begin(), cnt.end(), 0);
-        for (int i = b; i < e; ++i) ++cnt[ct8[p->rowidx[i]] + 1];
-        int* sp = &segptr[(size_t)g * (T + 1)];
-        sp[0] = b;
-        for (int t = 0; t < T; ++t) sp[t + 1] = sp[t] + cnt[t + 1];
-        for (int t = 0; t < T; ++t) cnt[t] = sp[t];
-        for (int i = b; i < e; ++i) {
-          int dst = cnt[ct8[p->rowidx[i]]]++;
-          rows_s[dst] = p->rowidx[i];
-          vals_s[dst] = p->values[i];
-        }
+      // host threads over contiguous gene ranges of about equal nnz (the counting sort is O(nnz) with random ct lookups)
+      const int n_thr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> workers;
+      int g_lo = 0;
+      for (int w = 0; w < n_thr; ++w) {
+        const long long target = (long long)h->nnz * (w + 1) / n_thr;
+        int g_hi = g_lo;
+        while (g_hi < G && (w == n_thr - 1 || p->colptr[g_hi + 1] <= target)) ++g_hi;
+        workers.emplace_back([&, g_lo, g_hi]() {
+          std::vector<int> cnt(T + 1);
+          for (int g = g_lo; g < g_hi; ++g) {
+            const int b = p->colptr[g], e = p->colptr[g + 1];
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int i = b; i < e; ++i) ++cnt[ct8[p->rowidx[i]] + 1];
+            int* sp = &segptr[(size_t)g * (T + 1)];
+            sp[0] = b;
+            for (int t = 0; t < T; ++t) sp[t + 1] = sp[t] + cnt[t + 1];
+            for (int t = 0; t < T; ++t) cnt[t] = sp[t];
+            for (int i = b; i < e; ++i) {
+              const int dst = cnt[ct8[p->rowidx[i]]]++;
+              rows_s[dst] = p->rowidx[i];
+              vals_s[dst] = p->values[i];
+            }
+          }
+        });
+        g_lo = g_hi;
       }
+      for (auto& t : workers) t.join();
       CU(h->segptr.upload(segptr.data(), segptr.size(), s));
       CU(h->rowidx_s.upload(rows_s.data(), h->nnz, s));
       CU(h->values_s.upload(vals_s.data(), h->nnz, s));
