@@ -148,6 +148,29 @@ void scdc_release(scdc_handle* handle);
  * group index = cond_code * T + ct_code. Either output may be NULL. */
 int scdc_group_means(scdc_handle* handle, double* means, double* detection_rate);
 
+/* (Re)install the tested rows on a handle: sub_cci_template_iter + observed vectors (reference
+ * R/utils_permutation.R:11-64). Lets one resident handle serve the observed pass first (create it with n_rows = 0), then
+ * the permutation test; only the genes the rows reference are reduced afterwards (the reference's gene subset, :79-84). */
+int scdc_set_rows(scdc_handle* handle, int32_t n_rows, const int32_t* row_lri, const int32_t* row_emit,
+                  const int32_t* row_recv, const double* observed);
+
+/* Observed pass over n template rows (reference run_simple_cci_analysis(compute_fast = FALSE), R/utils_cci.R:171-283,
+ * SURVEY.md "next" item f2): every output is caller-allocated, column-major over the n rows, and may be NULL.
+ *   expression / detection_rate [n x (C * nS)]: column c * nS + s = subunit s (L_1..L_nL, R_1..R_nR) in condition c, taken in
+ *       the emitter (ligands) / receiver (receptors); NaN = NA subunit          (L{i}_EXPRESSION*, R{j}_DETECTION_RATE* ...)
+ *   score [n x C]: CCI_SCORE per condition;  is_expressed [n x C]: IS_CCI_EXPRESSED per condition (is_detected_full with
+ *       threshold_pct / threshold_min_cells, R/utils_cci.R:783-802).
+ * LOGFC (a log of a score ratio) is left to the caller. */
+typedef struct scdc_observed {
+  double* expression;
+  double* detection_rate;
+  double* score;
+  uint8_t* is_expressed;
+} scdc_observed;
+int scdc_observed_pass(scdc_handle* handle, int64_t n, const int32_t* row_lri, const int32_t* row_emit,
+                       const int32_t* row_recv, double threshold_pct, double threshold_min_cells, int32_t score_type,
+                       scdc_observed* out);
+
 /* Debug / test hook: the labels scdc_run would draw on the device for replicates [perm_offset, perm_offset + n),
  * row-major [n][N]. cond_out may be NULL in detection mode. */
 int scdc_draw_labels(scdc_handle* handle, uint64_t seed, int64_t perm_offset, int64_t n, uint8_t* cond_out,

@@ -73,10 +73,33 @@ def _pmin(cols):
     return out
 
 
+def base_problem(ai):
+    """`PermutationProblem` holding the whole `analysis_inputs` (all LRI genes, no tested rows yet): what a resident
+    engine needs for the observed pass; the tested rows are installed later with `Engine.set_rows`."""
+    from .engine import PermutationProblem
+    enc = encode_inputs(ai)
+    X = ai["data_tr"].tocsc()
+    X.sort_indices()
+    C = 2 if ai["condition"]["is_cond"] else 1
+    ncols = 1 if C == 1 else 3 + ai["max_nL"] + ai["max_nR"]
+    return PermutationProblem(
+        n_cells=X.shape[0], n_genes=X.shape[1], n_celltypes=len(ai["cell_types"]), n_conditions=C,
+        max_nL=ai["max_nL"], max_nR=ai["max_nR"], colptr=X.indptr, rowidx=X.indices, values=X.data,
+        ct_code=enc["ct_code"], cond_code=enc["cond_code"], sub_gene=enc["sub_gene"],
+        row_lri=np.zeros(0, np.int32), row_emit=np.zeros(0, np.int32), row_recv=np.zeros(0, np.int32),
+        observed=np.zeros((0, ncols)))
+
+
 def run_simple_cci_analysis(ai, tmpl, score_type="geometric_mean", threshold_min_cells=5, threshold_pct=0.1,
-                            log_scale=False):
+                            log_scale=False, engine=None):
     """Observed pass (`compute_fast = FALSE`, R/utils_cci.R:171-439): expression, detection rate, CCI_SCORE*,
-    IS_CCI_EXPRESSED*, LOGFC. Returns a new table (dict of columns)."""
+    IS_CCI_EXPRESSED*, LOGFC. Returns a new table (dict of columns).
+
+    engine = None: NumPy on the host (what R does today). engine = an `Engine` built from `base_problem(ai)`: group means,
+    detection rates, gathers, scores and IS_CCI_EXPRESSED come from the GPU (`scdc_observed_pass`, SURVEY.md "next" f2);
+    only the LOGFC (a log) is finished on the host."""
+    if engine is not None:
+        return _run_simple_cci_analysis_b200(ai, tmpl, engine, score_type, threshold_min_cells, threshold_pct, log_scale)
     enc = encode_inputs(ai)
     T = len(ai["cell_types"])
     cond = ai["condition"]
@@ -110,6 +133,30 @@ def run_simple_cci_analysis(ai, tmpl, score_type="geometric_mean", threshold_min
                 ne, nr = tmpl[f"NCELLS_EMITTER{sfx[c]}"], tmpl[f"NCELLS_RECEIVER{sfx[c]}"]
                 out[f"IS_CCI_EXPRESSED{sfx[c]}"] = ((minL >= threshold_pct) & (minL * ne >= threshold_min_cells)
                                                     & (minR >= threshold_pct) & (minR * nr >= threshold_min_cells))
+    if C == 2:
+        s1, s2 = out[f"CCI_SCORE{sfx[0]}"], out[f"CCI_SCORE{sfx[1]}"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lfc = (s2 - s1) if log_scale else np.log(s2 / s1)
+        out["LOGFC"] = np.where(np.isnan(lfc), 0.0, lfc)
+        out["LOGFC_ABS"] = np.abs(out["LOGFC"])
+    return out
+
+
+def _run_simple_cci_analysis_b200(ai, tmpl, engine, score_type, threshold_min_cells, threshold_pct, log_scale):
+    cond = ai["condition"]
+    C = 2 if cond["is_cond"] else 1
+    nL, nR = ai["max_nL"], ai["max_nR"]
+    res = engine.observed_pass(tmpl["LRI_IDX"], tmpl["EMITTER_CODE"], tmpl["RECEIVER_CODE"], score_type=score_type,
+                               threshold_min_cells=threshold_min_cells, threshold_pct=threshold_pct)
+    out = dict(tmpl)
+    sfx = [""] if C == 1 else [f"_{cond['cond1']}", f"_{cond['cond2']}"]
+    for c in range(C):
+        for s in range(nL + nR):
+            name = f"L{s + 1}" if s < nL else f"R{s - nL + 1}"
+            out[f"{name}_EXPRESSION{sfx[c]}"] = np.ascontiguousarray(res["expression"][:, c, s])
+            out[f"{name}_DETECTION_RATE{sfx[c]}"] = np.ascontiguousarray(res["detection_rate"][:, c, s])
+        out[f"CCI_SCORE{sfx[c]}"] = np.ascontiguousarray(res["score"][:, c])
+        out[f"IS_CCI_EXPRESSED{sfx[c]}"] = np.ascontiguousarray(res["is_expressed"][:, c])
     if C == 2:
         s1, s2 = out[f"CCI_SCORE{sfx[0]}"], out[f"CCI_SCORE{sfx[1]}"]
         with np.errstate(divide="ignore", invalid="ignore"):

@@ -63,14 +63,22 @@ int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-// device buffer with RAII
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) with the release threshold
+// lifted, so the GB-sized work buffers of one call are recycled by the next instead of going through cudaMalloc / cudaFree
+// (measured 30-600 ms and erratic per call on a shared host). Allocation and free are ordered on the calling thread's
+// "allocation stream" (the handle's stream, set by every API entry point); other streams are made to wait on it.
+thread_local cudaStream_t g_alloc_stream = nullptr;
+thread_local bool g_alloc_async = false;
+
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
   ~DBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (g_alloc_async) cudaFreeAsync(p, g_alloc_stream); else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
@@ -78,7 +86,7 @@ struct DBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    return g_alloc_async ? cudaMallocAsync(&p, count * sizeof(T), g_alloc_stream) : cudaMalloc(&p, count * sizeof(T));
   }
   cudaError_t ensure(size_t count) { return (count <= n && p) ? cudaSuccess : alloc(count); }
   cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
@@ -86,6 +94,17 @@ struct DBuf {
     if (e != cudaSuccess || count == 0) return e;
     return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
   }
+};
+
+// every API entry point that touches device memory of a handle opens one of these
+struct AllocScope {
+  cudaStream_t prev_s;
+  bool prev_a;
+  explicit AllocScope(cudaStream_t s) : prev_s(g_alloc_stream), prev_a(g_alloc_async) {
+    g_alloc_stream = s;
+    g_alloc_async = !getenv("SCDC_NO_POOL");
+  }
+  ~AllocScope() { g_alloc_stream = prev_s; g_alloc_async = prev_a; }
 };
 
 }  // namespace
@@ -116,6 +135,10 @@ struct scdc_handle {
   DBuf<int> flag;
   double ms_upload = 0;
   size_t mem_total = 0;
+  // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
+  std::vector<int> sub_gene_h, gene_nnz_h;
+  int n_active = 0;        // genes referenced by the installed rows (gene_order holds them, heaviest first)
+  size_t nnz_active = 0;
   // labels of super-batch 0 drawn ahead of scdc_run (one-shot path: K1 overlaps the H2D of the matrix)
   struct Pre {
     bool valid = false;
@@ -128,6 +151,7 @@ struct scdc_handle {
 
 namespace {
 
+constexpr int kScoreThreads = 256, kScoreRPT = 2;
 int prelaunch_labels(scdc_handle* h, const scdc_options* o);
 
 int count_sm100_devices(std::vector<int>* ids) {
@@ -229,7 +253,6 @@ int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* 
   return SCDC_OK;
 }
 
-constexpr int kScoreThreads = 256, kScoreRPT = 2;
 
 }  // namespace
 
@@ -242,12 +265,109 @@ int scdc_device_count(void) { return count_sm100_devices(nullptr); }
 void scdc_release(scdc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamDestroy(h->stream);
-  if (h->stream_labels) cudaStreamDestroy(h->stream_labels);
-  if (h->stream_score) cudaStreamDestroy(h->stream_score);
-  if (h->pre.t0) cudaEventDestroy(h->pre.t0);
-  if (h->pre.t1) cudaEventDestroy(h->pre.t1);
-  delete h;
+  cudaStream_t s0 = h->stream, s1 = h->stream_labels, s2 = h->stream_score;
+  cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1;
+  {
+    AllocScope scope(s0);
+    if (!s0) g_alloc_async = false;
+    delete h;  // buffers go back to the pool in stream order
+  }
+  if (s0) { cudaStreamSynchronize(s0); cudaStreamDestroy(s0); }
+  if (s1) cudaStreamDestroy(s1);
+  if (s2) cudaStreamDestroy(s2);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+}
+
+// Installs the tested rows (sub_cci_template_iter + observed vectors) on a handle: row tables, NA mask, K3 work list,
+// product thresholds, factorisation table of the subunit columns, and the list of ACTIVE genes (the genes the rows
+// reference — the reference's gene subset of data_tr, R/utils_permutation.R:79-84 — heaviest column first).
+static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv,
+                        const double* observed) {
+  cudaStream_t s = h->stream;
+  const int T = h->T, C = h->C, G = h->G;
+  h->R = n_rows;
+  PhaseTimer pt;
+  CU(h->row_lri.upload(row_lri, n_rows, s));
+  CU(h->row_emit.upload(row_emit, n_rows, s));
+  CU(h->row_recv.upload(row_recv, n_rows, s));
+  CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
+  h->obs_na.resize((size_t)n_rows * h->ncols);
+  for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
+  // active genes
+  std::vector<uint8_t> lri_used((size_t)h->L, 0), gene_used((size_t)G, 0);
+  for (int r = 0; r < n_rows; ++r) lri_used[row_lri[r]] = 1;
+  for (int l = 0; l < h->L; ++l)
+    if (lri_used[l])
+      for (int k = 0; k < h->nS; ++k) {
+        const int g = h->sub_gene_h[(size_t)l * h->nS + k];
+        if (g >= 0) gene_used[g] = 1;
+      }
+  std::vector<int> order;
+  h->nnz_active = 0;
+  for (int g = 0; g < G; ++g)
+    if (gene_used[g] || n_rows == 0) { order.push_back(g); h->nnz_active += (size_t)h->gene_nnz_h[g]; }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->gene_nnz_h[a] > h->gene_nnz_h[b]; });
+  h->n_active = (int)order.size();
+  CU(h->gene_order.upload(order.data(), order.size(), s));
+  // K3 work list: rows stably sorted by LRI (counting sort), each LRI cut into slices of score_threads * kScoreRPT rows
+  std::vector<int> srow(n_rows), t_lri, t_beg, t_end;
+  {
+    std::vector<int> start((size_t)h->L + 1, 0);
+    for (int r = 0; r < n_rows; ++r) ++start[(size_t)row_lri[r] + 1];
+    for (int l = 0; l < h->L; ++l) start[(size_t)l + 1] += start[l];
+    for (int r = 0; r < n_rows; ++r) srow[start[row_lri[r]]++] = r;
+  }
+  h->score_threads = env_int("SCDC_SCORE_THREADS", kScoreThreads);
+  if (h->score_threads < 32 || h->score_threads > kScoreThreads || (h->score_threads & 31)) h->score_threads = kScoreThreads;
+  const int rpb = h->score_threads * kScoreRPT;
+  for (int b = 0; b < n_rows;) {
+    int e = b;
+    while (e < n_rows && row_lri[srow[e]] == row_lri[srow[b]]) ++e;
+    for (int c = b; c < e; c += rpb) {
+      t_lri.push_back(row_lri[srow[b]]);
+      t_beg.push_back(c);
+      t_end.push_back(std::min(e, c + rpb));
+    }
+    b = e;
+  }
+  h->n_tasks = (int)t_lri.size();
+  pt.lap("rows: K3 work list");
+  CU(h->thr.alloc((size_t)n_rows * C + 1));
+  if (n_rows > 0) {  // product thresholds of the one-sided geometric columns, computed on the device (IEEE sqrt)
+    scdc::k_product_thresholds<<<(unsigned)(((size_t)n_rows * C + 255) / 256), 256, 0, s>>>(
+        (size_t)n_rows * C, h->obs.p + (C == 2 ? (size_t)n_rows : 0), h->thr.p);
+    CU(cudaGetLastError());
+  }
+  std::vector<double> obs_sub;
+  h->fact_ok = false;
+  if (C == 2 && (long long)T * h->nS <= 2 * kScoreThreads) {
+    // The subunit columns of a row depend only on (LRI, emitter) / (LRI, receiver). If the observed subunit
+    // differences agree bitwise across the rows sharing such a pair (true for tables built by the reference, where they
+    // are joins of the same group means), K3 counts them once per (cell type, subunit).
+    const size_t n_tab = (size_t)h->L * T * h->nS;
+    obs_sub.assign(n_tab, std::nan(""));
+    std::vector<uint8_t> seen(n_tab, 0);
+    bool ok = true;
+    for (int r = 0; r < n_rows && ok; ++r) {
+      for (int sidx = 0; sidx < h->nS; ++sidx) {
+        const int ctx = (sidx < h->nL) ? row_emit[r] : row_recv[r];
+        const size_t k = ((size_t)row_lri[r] * T + ctx) * h->nS + sidx;
+        const double v = observed[(size_t)(3 + sidx) * n_rows + r];
+        if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
+        else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
+      }
+    }
+    h->fact_ok = ok && !env_int("SCDC_NO_FACT", 0);
+    if (h->fact_ok) CU(h->obs_sub.upload(obs_sub.data(), n_tab, s));
+  }
+  CU(h->srow.upload(srow.data(), srow.size(), s));
+  CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
+  CU(h->task_beg.upload(t_beg.data(), t_beg.size(), s));
+  CU(h->task_end.upload(t_end.data(), t_end.size(), s));
+  pt.lap("rows: enqueue rest");
+  CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+  return SCDC_OK;
 }
 
 // o_hint != NULL (one-shot path): the options of the run that follows. The cheap part of the validation has been done by
@@ -283,6 +403,13 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
   h->ncols = (h->C == 2) ? 3 + h->nS : 1;
   h->nnz = (size_t)p->colptr[h->G];
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  AllocScope alloc_scope(h->stream);
+  if (g_alloc_async) {  // keep freed work buffers in the device's default pool for the next call
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   {  // label generation runs one batch ahead with few, long-lived warps: give its blocks scheduling priority
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -311,12 +438,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     }
     std::vector<double> ngd(K);
     for (int k = 0; k < K; ++k) ngd[k] = (double)ng[k];
-    // gene order: heaviest columns first (tail balance)
-    std::vector<int> order(G);
-    for (int g = 0; g < G; ++g) order[g] = g;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return (p->colptr[a + 1] - p->colptr[a]) > (p->colptr[b + 1] - p->colptr[b]);
-    });
     // K1 visit order: differential mode walks the cells grouped by cell type (stable), detection mode in cell order
     std::vector<int> visit, ct_seg;
     if (C == 2) {
@@ -334,7 +455,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     CU(h->cond.upload(cond8.data(), N, s));
     CU(h->ngroup.upload(ngd.data(), K, s));
     CU(h->expect.upload(ng.data(), K, s));
-    CU(h->gene_order.upload(order.data(), G, s));
     pt.lap("create: context + small prep");
     if (o_hint) {  // K1 needs only the labels: draw the first super-batch while the matrix is copied
       rc = prelaunch_labels(h.get(), o_hint);
@@ -351,12 +471,9 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       }
     }
     CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
-    CU(h->row_lri.upload(p->row_lri, h->R, s));
-    CU(h->row_emit.upload(p->row_emit, h->R, s));
-    CU(h->row_recv.upload(p->row_recv, h->R, s));
-    CU(h->obs.upload(p->observed, (size_t)h->R * h->ncols, s));
-    h->obs_na.resize((size_t)h->R * h->ncols);
-    for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(p->observed[i]) ? 1 : 0;
+    h->sub_gene_h.assign(p->sub_gene, p->sub_gene + (size_t)h->L * h->nS);
+    h->gene_nnz_h.resize(G);
+    for (int g = 0; g < G; ++g) h->gene_nnz_h[g] = p->colptr[g + 1] - p->colptr[g];
     pt.lap("create: enqueue uploads");
     std::vector<int> segptr, rows_s;
     std::vector<double> vals_s;
@@ -399,59 +516,8 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     }
     // K3 v2 work list: rows stably sorted by LRI, each LRI cut into slices of kScoreThreads * kScoreRPT rows
     pt.lap("create: pass-1 matrix copy");
-    std::vector<int> srow(h->R), t_lri, t_beg, t_end;
-    {  // counting sort by LRI (stable)
-      std::vector<int> start((size_t)h->L + 1, 0);
-      for (int r = 0; r < h->R; ++r) ++start[(size_t)p->row_lri[r] + 1];
-      for (int l = 0; l < h->L; ++l) start[(size_t)l + 1] += start[l];
-      for (int r = 0; r < h->R; ++r) srow[start[p->row_lri[r]]++] = r;
-    }
-    h->score_threads = env_int("SCDC_SCORE_THREADS", kScoreThreads);
-    if (h->score_threads < 32 || h->score_threads > kScoreThreads || (h->score_threads & 31)) h->score_threads = kScoreThreads;
-    const int rpb = h->score_threads * kScoreRPT;
-    for (int b = 0; b < h->R;) {
-      int e = b;
-      while (e < h->R && p->row_lri[srow[e]] == p->row_lri[srow[b]]) ++e;
-      for (int c = b; c < e; c += rpb) {
-        t_lri.push_back(p->row_lri[srow[b]]);
-        t_beg.push_back(c);
-        t_end.push_back(std::min(e, c + rpb));
-      }
-      b = e;
-    }
-    h->n_tasks = (int)t_lri.size();
-    pt.lap("create: K3 work list");
-    CU(h->thr.alloc((size_t)h->R * C + 1));
-    if (h->R > 0) {  // product thresholds of the one-sided geometric columns, computed on the device (IEEE sqrt)
-      scdc::k_product_thresholds<<<(unsigned)(((size_t)h->R * C + 255) / 256), 256, 0, s>>>(
-          (size_t)h->R * C, h->obs.p + (C == 2 ? (size_t)h->R : 0), h->thr.p);
-      CU(cudaGetLastError());
-    }
-    std::vector<double> obs_sub;
-    if (C == 2 && (long long)T * h->nS <= 2 * kScoreThreads) {
-      // The subunit columns of a row depend only on (LRI, emitter) / (LRI, receiver). If the observed subunit
-      // differences agree bitwise across the rows sharing such a pair (true for tables built by the reference, where they
-      // are joins of the same group means), K3 counts them once per (cell type, subunit).
-      const size_t n_tab = (size_t)h->L * T * h->nS;
-      obs_sub.assign(n_tab, std::nan(""));
-      std::vector<uint8_t> seen(n_tab, 0);
-      bool ok = true;
-      for (int r = 0; r < h->R && ok; ++r) {
-        for (int sidx = 0; sidx < h->nS; ++sidx) {
-          const int ctx = (sidx < h->nL) ? p->row_emit[r] : p->row_recv[r];
-          const size_t k = ((size_t)p->row_lri[r] * T + ctx) * h->nS + sidx;
-          const double v = p->observed[(size_t)(3 + sidx) * h->R + r];
-          if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
-          else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
-        }
-      }
-      h->fact_ok = ok && !env_int("SCDC_NO_FACT", 0);
-      if (h->fact_ok) CU(h->obs_sub.upload(obs_sub.data(), n_tab, s));
-    }
-    CU(h->srow.upload(srow.data(), srow.size(), s));
-    CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
-    CU(h->task_beg.upload(t_beg.data(), t_beg.size(), s));
-    CU(h->task_end.upload(t_end.data(), t_end.size(), s));
+    rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
+    if (rc) return rc;
     CU(h->flag.alloc(1));
     pt.lap("create: enqueue rest");
     CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
@@ -531,7 +597,7 @@ cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bp
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
-  dim3 grid(h->G, (nCJ + pl.W - 1) / pl.W);
+  dim3 grid(h->n_active, (nCJ + pl.W - 1) / pl.W);  // active genes only (gene_order)
   kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
                                         h->ngroup.p, h->gene_order.p, M2);
   return cudaGetLastError();
@@ -598,6 +664,7 @@ int prelaunch_labels(scdc_handle* h, const scdc_options* o) {
 // h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
 int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st, cudaStream_t s) {
   CU(cudaSetDevice(h->device));
+  AllocScope alloc_scope(h->stream);
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K, R = h->R;
   const int B = pick_batch(h, o);
   const int Bw = B / 32;
@@ -632,13 +699,20 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(h->M2[i].ensure(msz));
   }
   CU(h->counts.ensure((size_t)R * h->ncols + 1));
-  CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
   if (uploaded) {
     CU(h->up_ct.ensure((size_t)B * N));
     if (C == 2) CU(h->up_cond.ensure((size_t)B * N));
-    CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
   }
   if (dist_host) CU(h->dist.ensure((size_t)B * ncols_d * R));
+  if (s != h->stream) {  // buffers are (re)allocated in the order of the handle's stream: the caller's stream waits for it
+    cudaEvent_t dep;
+    CU(cudaEventCreateWithFlags(&dep, cudaEventDisableTiming));
+    cudaError_t e1 = cudaEventRecord(dep, h->stream), e2 = cudaStreamWaitEvent(s, dep, 0);
+    cudaEventDestroy(dep);
+    CU(e1); CU(e2);
+  }
+  CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
+  if (uploaded) CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
   std::vector<cudaEvent_t> evs, evl;  // timing events on the compute stream (3 per batch) / label stream (2 per batch)
   auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st_) -> cudaError_t {
     cudaEvent_t e;
@@ -746,8 +820,8 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(mark(evs, s));
     if (C == 2) {
       const int nWC = B / 128, W = 8;
-      const long long tasks = (long long)G * nWC;
-      scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, T, nWC, h->segptr.p, h->rowidx_s.p,
+      const long long tasks = (long long)h->n_active * nWC;
+      scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p,
                                                                            h->values_s.p, bits1_b, SBw, h->ngroup.p,
                                                                            h->gene_order.p, M1b);
       CU(cudaGetLastError());
@@ -760,8 +834,8 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     ++launches; ++reduce_launches;
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
-    reduce_bytes += (double)C * ((double)h->nnz * (sv + 4.0) + 4.0 * (G + 1)) + (double)B * N * (C == 2 ? 1.125 : 1.0) +
-                    (double)C * B * K * G * sv;
+    reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
+                    (double)B * N * (C == 2 ? 1.125 : 1.0) + (double)C * B * K * h->n_active * sv;
     CU(mark(evs, s));
     if (overlap_score) {
       CU(cudaEventRecord(m_ready[mb], s));
@@ -1104,6 +1178,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
 int scdc_group_means(scdc_handle* h, double* means, double* detection_rate) {
   if (!h) return fail(SCDC_EINVAL, "handle is NULL");
   CU(cudaSetDevice(h->device));
+  AllocScope alloc_scope(h->stream);
   DBuf<double> out;
   const size_t n = (size_t)h->K * h->G;
   CU(out.alloc(n));
@@ -1117,6 +1192,94 @@ int scdc_group_means(scdc_handle* h, double* means, double* detection_rate) {
     CU(cudaMemcpyAsync(dst, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
+  return SCDC_OK;
+}
+
+int scdc_set_rows(scdc_handle* h, int32_t n_rows, const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv,
+                  const double* observed) {
+  if (!h) return fail(SCDC_EINVAL, "handle is NULL");
+  if (n_rows < 0 || (n_rows > 0 && (!row_lri || !row_emit || !row_recv || !observed)))
+    return fail(SCDC_EINVAL, "bad rows");
+  for (int r = 0; r < n_rows; ++r) {
+    if (row_lri[r] < 0 || row_lri[r] >= h->L || row_emit[r] < 0 || row_emit[r] >= h->T || row_recv[r] < 0 || row_recv[r] >= h->T)
+      return fail(SCDC_EINVAL, "row %d has an out-of-range LRI / emitter / receiver code", r);
+    const int l = row_lri[r];
+    if (h->sub_gene_h[(size_t)l * h->nS] < 0 || h->sub_gene_h[(size_t)l * h->nS + h->nL] < 0)
+      return fail(SCDC_EINVAL, "row %d: LRI %d lacks LIGAND_1 or RECEPTOR_1", r, l);
+  }
+  CU(cudaSetDevice(h->device));
+  AllocScope alloc_scope(h->stream);
+  h->pre.valid = false;
+  try {
+    return install_rows(h, n_rows, row_lri, row_emit, row_recv, observed);
+  } catch (const std::bad_alloc&) {
+    return fail(SCDC_ENOMEM, "host allocation failed while staging the rows");
+  }
+}
+
+int scdc_observed_pass(scdc_handle* h, int64_t n, const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv,
+                       double threshold_pct, double threshold_min_cells, int32_t score_type, scdc_observed* out) {
+  if (!h || !out) return fail(SCDC_EINVAL, "handle or out is NULL");
+  if (n < 0 || (n > 0 && (!row_lri || !row_emit || !row_recv))) return fail(SCDC_EINVAL, "bad rows");
+  if (score_type != SCDC_SCORE_GEOMETRIC && score_type != SCDC_SCORE_ARITHMETIC)
+    return fail(SCDC_EINVAL, "unknown score_type %d", score_type);
+  for (int64_t r = 0; r < n; ++r) {
+    if (row_lri[r] < 0 || row_lri[r] >= h->L || row_emit[r] < 0 || row_emit[r] >= h->T || row_recv[r] < 0 || row_recv[r] >= h->T)
+      return fail(SCDC_EINVAL, "row %lld has an out-of-range LRI / emitter / receiver code", (long long)r);
+  }
+  CU(cudaSetDevice(h->device));
+  AllocScope alloc_scope(h->stream);
+  cudaStream_t s = h->stream;
+  const int K = h->K, G = h->G, C = h->C, nS = h->nS;
+  DBuf<double> means, drate;
+  CU(means.alloc((size_t)K * G));
+  CU(drate.alloc((size_t)K * G));
+  for (int mode = 0; mode < 2; ++mode) {
+    scdc::k_group_means<<<(G + 127) / 128, 128, 0, s>>>(G, K, h->T, h->colptr.p, h->rowidx.p, h->values.p, h->ct.p,
+                                                        C == 2 ? h->cond.p : nullptr, h->ngroup.p, mode,
+                                                        mode == 0 ? means.p : drate.p);
+    CU(cudaGetLastError());
+  }
+  const int64_t chunk = 1 << 20;  // rows per device chunk
+  const int nc = (int)std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
+  DBuf<int> d_lri, d_emit, d_recv;
+  DBuf<double> d_expr, d_dr, d_score;
+  DBuf<unsigned char> d_is;
+  CU(d_lri.alloc(nc)); CU(d_emit.alloc(nc)); CU(d_recv.alloc(nc));
+  CU(d_expr.alloc((size_t)nc * C * nS)); CU(d_dr.alloc((size_t)nc * C * nS)); CU(d_score.alloc((size_t)nc * C));
+  CU(d_is.alloc((size_t)nc * C));
+  for (int64_t b = 0; b < n; b += chunk) {
+    const int m = (int)std::min<int64_t>(chunk, n - b);
+    CU(cudaMemcpyAsync(d_lri.p, row_lri + b, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_emit.p, row_emit + b, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_recv.p, row_recv + b, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+    scdc::ObservedArgs A;
+    A.n = m; A.T = h->T; A.C = C; A.nL = h->nL; A.nS = nS; A.score_type = score_type;
+    A.threshold_pct = threshold_pct; A.threshold_min_cells = threshold_min_cells;
+    A.row_lri = d_lri.p; A.row_emit = d_emit.p; A.row_recv = d_recv.p; A.sub_gene = h->sub_gene.p;
+    A.means = means.p; A.drate = drate.p; A.ngroup = h->ngroup.p;
+    A.expr = d_expr.p; A.dr = d_dr.p; A.score = d_score.p; A.is_expr = d_is.p;
+    scdc::k_observed_rows<<<(m + 255) / 256, 256, 0, s>>>(A);
+    CU(cudaGetLastError());
+    // device chunks are column-major over m rows; the caller's arrays are column-major over n rows
+    for (int col = 0; col < C * nS; ++col) {
+      if (out->expression)
+        CU(cudaMemcpyAsync(out->expression + (size_t)col * n + b, d_expr.p + (size_t)col * m, (size_t)m * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+      if (out->detection_rate)
+        CU(cudaMemcpyAsync(out->detection_rate + (size_t)col * n + b, d_dr.p + (size_t)col * m, (size_t)m * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+    }
+    for (int c = 0; c < C; ++c) {
+      if (out->score)
+        CU(cudaMemcpyAsync(out->score + (size_t)c * n + b, d_score.p + (size_t)c * m, (size_t)m * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+      if (out->is_expressed)
+        CU(cudaMemcpyAsync(out->is_expressed + (size_t)c * n + b, d_is.p + (size_t)c * m, (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+  }
+  CU(cudaStreamSynchronize(s));
   return SCDC_OK;
 }
 
@@ -1140,6 +1303,7 @@ int scdc_draw_labels(scdc_handle* h, uint64_t seed, int64_t perm_offset, int64_t
   if (!h || !ct_out) return fail(SCDC_EINVAL, "handle or ct_out is NULL");
   if (n < 1 || perm_offset < 0) return fail(SCDC_EINVAL, "n must be >= 1 and perm_offset >= 0");
   CU(cudaSetDevice(h->device));
+  AllocScope alloc_scope(h->stream);
   cudaStream_t s = h->stream;
   const int N = h->N, C = h->C;
   const int B = 128;

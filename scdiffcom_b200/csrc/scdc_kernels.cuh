@@ -258,7 +258,7 @@ __device__ __forceinline__ double entry_value(const uint4& e) {
 // kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 128 replicates
 // (4 per lane): one uniform 16-byte load brings the condition bits of a cell for all 128.
 // M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
-// grid.x = G * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
+// grid.x = nGa * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
 // ------------------------------------------------------------------------------------------------------------------
 // acc1 += v if sel != 0 else acc0 += v, written as two fused multiply-adds with a 1.0 / 0.0 selector: v * 1.0 + acc is
 // exactly acc + v (the product is exact, one rounding) and v * 0.0 + acc leaves acc unchanged, so the result is bit-identical
@@ -270,7 +270,7 @@ __device__ __forceinline__ void sel_add(double& acc1, double& acc0, uint32_t sel
   acc0 = fma(v, b0, acc0);
 }
 
-__global__ void __launch_bounds__(256) k_pass1_cond(int G, int T, int nWC, const int* __restrict__ segptr,
+__global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
                                                     const int* __restrict__ rowidx_s, const double* __restrict__ values_s,
                                                     const uint32_t* __restrict__ bits1, int Bw,
                                                     const double* __restrict__ ngroup, const int* __restrict__ gene_order,
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_pass1_cond(int G, int T, int nWC, const
   __shared__ uint4 stage_all[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   const long long task = (long long)blockIdx.x * W + warp;
-  if (task >= (long long)G * nWC) return;
+  if (task >= (long long)nGa * nWC) return;  // nGa active genes (gene_order), G = layout stride of M1
   const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
   uint4* stage = stage_all[warp];
   const int K = 2 * T;
@@ -1017,6 +1017,58 @@ __global__ void k_product_thresholds(size_t n, const double* __restrict__ obs, d
     }
   }
   thr[i] = y;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Observed pass over template rows (reference run_simple_cci_analysis(compute_fast = FALSE), R/utils_cci.R:171-283):
+// per row and condition gather the subunit means and detection rates of the emitter (ligands) / receiver (receptors),
+// complex-min, CCI_SCORE and IS_CCI_EXPRESSED (is_detected_full, R/utils_cci.R:783-802). One thread per row; outputs are
+// column-major over the n rows of this chunk. means / drate: [G][K] (K = C * T, k = cond * T + ct).
+// ------------------------------------------------------------------------------------------------------------------
+struct ObservedArgs {
+  int n, T, C, nL, nS, score_type;
+  double threshold_pct, threshold_min_cells;
+  const int* row_lri;
+  const int* row_emit;
+  const int* row_recv;
+  const int* sub_gene;
+  const double* means;
+  const double* drate;
+  const double* ngroup;
+  double* expr;           // [C * nS][n]
+  double* dr;             // [C * nS][n]
+  double* score;          // [C][n]
+  unsigned char* is_expr; // [C][n]
+};
+
+__global__ void k_observed_rows(ObservedArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int l = A.row_lri[i], e = A.row_emit[i], r = A.row_recv[i];
+  const int K = A.C * A.T;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int c = 0; c < A.C; ++c) {
+    double mL = 0.0, mR = 0.0, dL = 0.0, dR = 0.0;
+    bool hL = false, hR = false;
+    for (int s = 0; s < A.nS; ++s) {
+      const int g = A.sub_gene[l * A.nS + s];
+      const bool isL = s < A.nL;
+      double v = nan, d = nan;
+      if (g >= 0) {
+        const size_t idx = (size_t)g * K + c * A.T + (isL ? e : r);
+        v = A.means[idx];
+        d = A.drate[idx];
+        if (isL) { mL = hL ? fmin(mL, v) : v; dL = hL ? fmin(dL, d) : d; hL = true; }
+        else { mR = hR ? fmin(mR, v) : v; dR = hR ? fmin(dR, d) : d; hR = true; }
+      }
+      A.expr[(size_t)(c * A.nS + s) * A.n + i] = v;
+      A.dr[(size_t)(c * A.nS + s) * A.n + i] = d;
+    }
+    A.score[(size_t)c * A.n + i] = A.score_type == 0 ? sqrt(mL * mR) : (mL + mR) / 2;
+    const double ne = A.ngroup[c * A.T + e], nr = A.ngroup[c * A.T + r];
+    A.is_expr[(size_t)c * A.n + i] = (dL >= A.threshold_pct && dL * ne >= A.threshold_min_cells &&
+                                      dR >= A.threshold_pct && dR * nr >= A.threshold_min_cells) ? 1 : 0;
+  }
 }
 
 __global__ void k_widen_counts(size_t n, const uint32_t* __restrict__ in, long long* __restrict__ out) {

@@ -202,6 +202,32 @@ class Engine:
         check(self._lib.scdc_group_means(self._h, _ptr(means), _ptr(dr)))
         return (means, dr) if detection_rate else means
 
+    def set_rows(self, row_lri, row_emit, row_recv, observed):
+        """(Re)install the tested rows + observed vectors on the resident handle (`scdc_set_rows`)."""
+        pr = self.problem
+        pr.row_lri, pr.row_emit, pr.row_recv = _arr(row_lri, np.int32), _arr(row_emit, np.int32), _arr(row_recv, np.int32)
+        obs = np.asfortranarray(np.asarray(observed, dtype=np.float64).reshape(pr.n_rows, pr.ncols))
+        pr.observed = obs
+        check(self._lib.scdc_set_rows(self._h, pr.n_rows, _ptr(pr.row_lri), _ptr(pr.row_emit), _ptr(pr.row_recv), _ptr(obs)))
+
+    def observed_pass(self, row_lri, row_emit, row_recv, score_type="geometric_mean", threshold_min_cells=5,
+                      threshold_pct=0.1):
+        """Observed pass over template rows on the GPU (`scdc_observed_pass`): dict(expression [n, C, nS],
+        detection_rate [n, C, nS], score [n, C], is_expressed [n, C] bool)."""
+        pr = self.problem
+        lri, em, rc = _arr(row_lri, np.int32), _arr(row_emit, np.int32), _arr(row_recv, np.int32)
+        n, Cn, nS = len(lri), pr.n_conditions, pr.max_nL + pr.max_nR
+        expr = np.zeros((Cn * nS, n), dtype=np.float64)
+        dr = np.zeros((Cn * nS, n), dtype=np.float64)
+        score = np.zeros((Cn, n), dtype=np.float64)
+        is_e = np.zeros((Cn, n), dtype=np.uint8)
+        out = _lib.Observed(_ptr(expr), _ptr(dr), _ptr(score), _ptr(is_e))
+        st = SCORE_TYPES[score_type] if isinstance(score_type, str) else int(score_type)
+        check(self._lib.scdc_observed_pass(self._h, n, _ptr(lri), _ptr(em), _ptr(rc), float(threshold_pct),
+                                           float(threshold_min_cells), st, C.byref(out)))
+        return {"expression": expr.reshape(Cn, nS, n).transpose(2, 0, 1), "detection_rate": dr.reshape(Cn, nS, n).transpose(2, 0, 1),
+                "score": score.T, "is_expressed": is_e.T.astype(bool)}
+
     def draw_labels(self, n, seed=42, perm_offset=0):
         """The label matrices the device generator produces for replicates [perm_offset, perm_offset + n)."""
         pr = self.problem

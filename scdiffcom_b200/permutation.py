@@ -54,6 +54,15 @@ def observed_matrix(ai, cci_dt_simple, mask):
     return np.stack(cols, axis=1)
 
 
+def tested_row_arrays(ai, cci_dt_simple):
+    """(mask, row_lri, row_emit, row_recv, observed) of the tested rows, with gene / LRI indices of the FULL inputs."""
+    mask = tested_rows(ai, cci_dt_simple)
+    obs = observed_matrix(ai, cci_dt_simple, mask)
+    return (mask, np.asarray(cci_dt_simple["LRI_IDX"])[mask].astype(np.int32),
+            np.asarray(cci_dt_simple["EMITTER_CODE"])[mask].astype(np.int32),
+            np.asarray(cci_dt_simple["RECEIVER_CODE"])[mask].astype(np.int32), obs)
+
+
 def build_problem(ai, cci_dt_simple):
     """Everything `.Call` receives: returns (PermutationProblem, tested-row mask)."""
     mask = tested_rows(ai, cci_dt_simple)
@@ -93,24 +102,34 @@ def pvalue_column_names(ai):
 
 def run_stat_analysis(analysis_inputs, cci_dt_simple, iterations, return_distributions=False,
                       score_type="geometric_mean", verbose=False, *, seed=42, n_gpus=1, perm_cond=None, perm_ct=None,
-                      batch_size=0):
+                      batch_size=0, engine=None):
     """Mirror of run_stat_analysis(analysis_inputs, cci_dt_simple, iterations, return_distributions, score_type, verbose)
     -> {"cci_raw": table with the P_VALUE* columns added, "distributions": {...}, "stats": engine timings}.
 
     Keyword-only extras are out-of-band backend knobs (the reference's parameter list cannot grow):
     `seed` (the reference seeds through set.seed() in run_interaction_analysis), `n_gpus`, `batch_size`, and
     `perm_cond` / `perm_ct` = uploaded label matrices [replicates, cells] for validation against the reference's own
-    shuffles.
+    shuffles. `engine`: an `Engine` already resident on a GPU with the whole `analysis_inputs` (`cci.base_problem`), e.g. the
+    one that ran the observed pass: the tested rows are installed on it (`scdc_set_rows`) instead of re-uploading the matrix.
     """
     ai = analysis_inputs
     iterations = int(iterations)
     n_run = iterations_to_run(iterations, return_distributions)
-    prob, mask = build_problem(ai, cci_dt_simple)
+    if engine is None:
+        prob, mask = build_problem(ai, cci_dt_simple)
+    else:
+        mask, r_lri, r_emit, r_recv, obs = tested_row_arrays(ai, cci_dt_simple)
+        engine.set_rows(r_lri, r_emit, r_recv, obs)
+        prob = engine.problem
     if verbose:
         print(f"Performing permutation analysis ({iterations} iterations by batches of {INTERNAL_ITER}) on "
               f"{prob.n_rows} potential CCIs.")
-    res = perm_counts(prob, n_run, seed=seed, score_type=score_type, n_gpus=n_gpus, batch_size=batch_size,
-                      perm_cond=perm_cond, perm_ct=perm_ct, return_distributions=return_distributions)
+    if engine is None:
+        res = perm_counts(prob, n_run, seed=seed, score_type=score_type, n_gpus=n_gpus, batch_size=batch_size,
+                          perm_cond=perm_cond, perm_ct=perm_ct, return_distributions=return_distributions)
+    else:
+        res = engine.run(n_run, seed=seed, score_type=score_type, batch_size=batch_size, perm_cond=perm_cond,
+                         perm_ct=perm_ct, return_distributions=return_distributions)
     pvals = res["counts"] / iterations                  # :215-259 (NaN where the subunit is NA, :442-469)
     out = dict(cci_dt_simple)
     n_full = len(mask)
@@ -125,7 +144,7 @@ def run_stat_analysis(analysis_inputs, cci_dt_simple, iterations, return_distrib
     distributions = {}
     if return_distributions:                            # :304-426: rows x (iterations + 1), last column = observed
         d = res["distributions"]                        # [iterations, ncols_d, R_sub]
-        obs = prob.observed.reshape(prob.n_rows, prob.ncols)
+        obs = np.asarray(prob.observed).reshape(prob.n_rows, prob.ncols)
         cond = ai["condition"]
         names = ["DISTRIBUTIONS"] if not cond["is_cond"] else [
             "DISTRIBUTIONS_DE", f"DISTRIBUTIONS_{cond['cond1']}", f"DISTRIBUTIONS_{cond['cond2']}"]

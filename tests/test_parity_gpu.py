@@ -205,3 +205,30 @@ def test_de_column_filter_is_exact():
     assert mismatches == 0
     assert bad_approx == 0
     assert fast > 10_000_000          # the fast path decides whenever the threshold is not within the band
+
+
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+@pytest.mark.parametrize("score_type", ["geometric_mean", "arithmetic_mean"])
+def test_observed_pass_on_gpu_and_one_resident_engine(liver, mode, score_type):
+    """SURVEY.md "next" f2: run_simple_cci_analysis(compute_fast = FALSE) on the GPU equals the host / oracle tables bit for
+    bit (expression, detection rate, CCI_SCORE*, IS_CCI_EXPRESSED*: the reference's known-answer columns,
+    tests/testthat/test-everything.R:377-490), and the same resident engine then runs the permutation test on the rows it
+    found (scdc_set_rows) with the counts of the one-shot call."""
+    from scdiffcom_b200 import cci, preprocessing
+    ai = helpers.liver_inputs(liver, mode, preprocessing)
+    tmpl = cci.create_cci_template(ai)
+    host = cci.run_simple_cci_analysis(ai, tmpl, score_type=score_type)
+    with Engine(cci.base_problem(ai)) as eng:
+        dev = cci.run_simple_cci_analysis(ai, tmpl, score_type=score_type, engine=eng)
+        assert set(dev) == set(host)
+        for k, v in host.items():
+            if k in ("LOGFC", "LOGFC_ABS"):
+                np.testing.assert_allclose(dev[k], v, rtol=1e-15, atol=0)
+            else:
+                assert np.array_equal(dev[k], v, equal_nan=True), k
+        a = run_stat_analysis(ai, dev, 300, False, score_type, False, seed=11, engine=eng)
+    b = run_stat_analysis(ai, host, 300, False, score_type, False, seed=11)
+    assert int(a["tested"].sum()) == (8952 if mode == "cond" else 7352)
+    for name in b["cci_raw"]:
+        if "P_VALUE" in name:
+            assert np.array_equal(a["cci_raw"][name], b["cci_raw"][name], equal_nan=True), name

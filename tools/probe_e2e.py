@@ -18,3 +18,12 @@ eng.run(10000, seed=1)
 run("with resident engine")
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 run("with torch stream")
+import subprocess
+sys.path.insert(0, "/root/repo")
+from bench import ClockSampler
+sm = ClockSampler(0); sm.start(); time.sleep(1.0); print(sm.stop(), file=sys.stderr)
+run("after sampler stop")
+p = subprocess.run(["pgrep", "-a", "nvidia-smi"], capture_output=True, text=True); print("pgrep:", p.stdout, file=sys.stderr)
+sm = ClockSampler(0); sm.start(); time.sleep(0.3)
+run("WHILE sampler runs")
+print(sm.stop(), file=sys.stderr)
