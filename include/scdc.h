@@ -181,6 +181,11 @@ int scdc_draw_labels(scdc_handle* handle, uint64_t seed, int64_t perm_offset, in
  * out[0] = mismatches (must be 0), out[1] = decisions taken by the fast path, out[2] = approximations outside 2^-20. */
 int scdc_selftest_de_filter(uint64_t n, uint64_t seed, uint64_t out[3]);
 
+/* Device work buffers are drawn from the device's default stream-ordered memory pool and kept there between calls
+ * (cudaMallocAsync with the release threshold lifted), so repeated calls do not pay cudaMalloc / cudaFree again.
+ * scdc_trim(device) hands the cached memory back to the driver (device = index among all CUDA devices, -1 = all). */
+int scdc_trim(int32_t device);
+
 const char* scdc_last_error(void); /* thread-local message of the last failing call on this thread */
 int scdc_device_count(void);       /* visible devices with compute capability 10.x (0 when there is none) */
 const char* scdc_version(void);

@@ -161,9 +161,10 @@ int oracle_group_means(int N, int G, int K, const int32_t* colptr, const int32_t
 }
 
 /* ---- restatement of the device label generator (scdc_kernels.cuh: k_draw_labels) ----------------------------------
- * Philox4x32-10, counter (visit, block, replicate lo, replicate hi), key = seed. Draw d (0 = condition, 1 = cell type) of
- * visit i, attempt a = word 2a + d of the visit's stream. Cells are visited in cell order (detection) or stably sorted by
- * cell type (differential). Sequential urn draws: next label k with probability remaining[k] / remaining total. */
+ * Philox4x32-10, key = seed. A visit makes D draws (D = 1: cell type; D = 2: condition then cell type). Draw d of visit v
+ * sits at word position pos = v * D + d: attempt 0 = element pos % 4 of block (pos / 4, 0, replicate lo, replicate hi);
+ * attempt a >= 1 = element 0 of block (pos, a, replicate). Cells are visited in cell order (detection) or stably sorted
+ * by cell type (differential). Sequential urn draws: next label k with probability remaining[k] / remaining total. */
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
   for (int r = 0; r < 10; ++r) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -173,16 +174,20 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-static uint32_t stream_word(uint32_t visit, int w, uint64_t rep, uint64_t seed) {
+static uint32_t stream_word(uint32_t pos, int attempt, uint64_t rep, uint64_t seed) {
   uint32_t o[4];
-  philox4x32_10(visit, (uint32_t)(w >> 2), (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
-  return o[w & 3];
+  if (attempt == 0) {
+    philox4x32_10(pos >> 2, 0u, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    return o[pos & 3];
+  }
+  philox4x32_10(pos, (uint32_t)attempt, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  return o[0];
 }
 /* Lemire's unbiased bounded integer: attempts a = 0, 1, .. until accepted */
-static uint32_t bounded_draw(uint32_t visit, int d, uint32_t range, uint64_t rep, uint64_t seed) {
+static uint32_t bounded_draw(uint32_t pos, uint32_t range, uint64_t rep, uint64_t seed) {
   const uint32_t t = (0u - range) % range;
   for (int a = 0;; ++a) {
-    uint64_t m = (uint64_t)stream_word(visit, 2 * a + d, rep, seed) * range;
+    uint64_t m = (uint64_t)stream_word(pos, a, rep, seed) * range;
     if ((uint32_t)m >= t) return (uint32_t)(m >> 32);
   }
 }
@@ -224,12 +229,12 @@ int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int3
       if (C == 2) {
         const int t = ct_code[i];
         const uint32_t r0 = remc[t], r1 = remc[(size_t)T + t];
-        const uint32_t u = bounded_draw((uint32_t)v, 0, r0 + r1, rep, seed);
+        const uint32_t u = bounded_draw((uint32_t)v * 2u, r0 + r1, rep, seed);
         c = (u < r0) ? 0 : 1;
         --remc[(size_t)c * T + t];
         cond_out[(size_t)q * N + i] = (uint8_t)c;
       }
-      const uint32_t u = bounded_draw((uint32_t)v, 1, tot[c], rep, seed);
+      const uint32_t u = bounded_draw((uint32_t)v * (uint32_t)C + (uint32_t)(C - 1), tot[c], rep, seed);
       --tot[c];
       ct_out[(size_t)q * N + i] = (uint8_t)urn_pick(urn + (size_t)c * T, T, u);
     }

@@ -5,7 +5,7 @@ R/utils_permutation.R:1-499) backed by hand-written CUDA kernels behind the C-AB
 Importing the package does not need a GPU; computing anything does (there is no CPU fallback).
 """
 from ._lib import ScdcError, LIB_PATH  # noqa: F401
-from .engine import Engine, PermutationProblem, device_count, perm_counts, version  # noqa: F401
+from .engine import Engine, PermutationProblem, device_count, perm_counts, trim, version  # noqa: F401
 from .permutation import run_stat_analysis  # noqa: F401
 
-__all__ = ["Engine", "PermutationProblem", "ScdcError", "device_count", "perm_counts", "run_stat_analysis", "version"]
+__all__ = ["Engine", "PermutationProblem", "ScdcError", "device_count", "perm_counts", "run_stat_analysis", "trim", "version"]

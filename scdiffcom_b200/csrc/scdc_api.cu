@@ -1283,6 +1283,20 @@ int scdc_observed_pass(scdc_handle* h, int64_t n, const int32_t* row_lri, const 
   return SCDC_OK;
 }
 
+int scdc_trim(int32_t device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(SCDC_ENOGPU, "no CUDA device"); }
+  for (int d = 0; d < n; ++d) {
+    if (device >= 0 && d != device) continue;
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, d));
+    CU(cudaSetDevice(d));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemPoolTrimTo(pool, 0));
+  }
+  return SCDC_OK;
+}
+
 int scdc_selftest_de_filter(uint64_t n, uint64_t seed, uint64_t out[3]) {
   if (!out || n == 0) return fail(SCDC_EINVAL, "out is NULL or n == 0");
   std::vector<int> ids;

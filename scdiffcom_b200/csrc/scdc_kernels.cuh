@@ -20,10 +20,12 @@
 namespace scdc {
 
 // ------------------------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11), counter-based: block(visit i, j) has counter (i, j, replicate lo, replicate hi)
-// and key = seed. Draw d (0 = condition, 1 = cell type) of visit i, attempt a, is word 2a + d of the visit's stream
-// (block j = (2a + d) / 4, element (2a + d) % 4): every draw is a pure function of (seed, replicate, visit, attempt),
-// so the generator has no sequential state and any replicate range can be regenerated anywhere.
+// Philox4x32-10 (Salmon et al., SC'11), counter-based, key = seed. A visit makes D draws (D = 1: cell type, detection
+// mode; D = 2: condition then cell type, differential mode). Draw d of visit v sits at word position pos = v * D + d of
+// the replicate's stream: attempt 0 reads element pos % 4 of block (c0 = pos / 4, c1 = 0, replicate lo, replicate hi);
+// a rejected attempt a >= 1 (probability < range / 2^32) reads element 0 of block (c0 = pos, c1 = a, replicate).
+// Every draw is a pure function of (seed, replicate, visit, attempt): no sequential generator state, any replicate
+// range can be regenerated anywhere, and one Philox block serves 4 / D consecutive visits.
 // ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t out[4]) {
@@ -38,26 +40,19 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// uniform integer in [0, range): Lemire's multiply-shift with rejection (exactly unbiased). blk0 = block (visit, 0).
-__host__ __device__ inline uint32_t bounded_draw(const uint32_t blk0[4], int d, uint32_t range, uint32_t visit, uint32_t r_lo,
-                                                 uint32_t r_hi, uint32_t k0, uint32_t k1) {
-  uint64_t m = (uint64_t)blk0[d] * range;
+// uniform integer in [0, range): Lemire's multiply-shift with rejection (exactly unbiased). w0 = the attempt-0 word.
+__host__ __device__ inline uint32_t bounded_draw(uint32_t w0, uint32_t pos, uint32_t range, uint32_t r_lo, uint32_t r_hi,
+                                                 uint32_t k0, uint32_t k1) {
+  uint64_t m = (uint64_t)w0 * range;
   uint32_t l = (uint32_t)m;
   if (l < range) {
     const uint32_t t = (0u - range) % range;
-    int a = 0;
-    while (l < t) {  // rejected (probability < range / 2^32): next attempt's word
+    uint32_t a = 0;
+    while (l < t) {  // rejected: next attempt's word
       ++a;
-      const int w = 2 * a + d;
-      uint32_t x;
-      if (w < 4) {
-        x = blk0[w];
-      } else {
-        uint32_t o[4];
-        philox4x32_10(visit, (uint32_t)(w >> 2), r_lo, r_hi, k0, k1, o);
-        x = o[w & 3];
-      }
-      m = (uint64_t)x * range;
+      uint32_t o[4];
+      philox4x32_10(pos, a, r_lo, r_hi, k0, k1, o);
+      m = (uint64_t)o[0] * range;
       l = (uint32_t)m;
     }
   }
@@ -113,8 +108,10 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
   }
   const int Bw = Bpad / 32;
   const int off2 = lab2_offset(q, J);
-  uint32_t blk[4];
+  const int D = C;  // draws per visit
+  uint32_t blk[4], nxt[4];
   philox4x32_10(0u, 0u, r_lo, r_hi, k0, k1, blk);
+  philox4x32_10(1u, 0u, r_lo, r_hi, k0, k1, nxt);  // the next block is always computed one block ahead, off the urn's chain
   int v = 0;
   const int n_seg = (C == 2) ? T : 1;
   for (int t = 0; t < n_seg; ++t) {
@@ -122,16 +119,26 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
     uint32_t r0 = 0, r1 = 0;
     if (C == 2) { r0 = ngroup_u[t]; r1 = ngroup_u[T + t]; }
     for (; v < v_end; ++v) {
-      uint32_t nxt[4];
-      philox4x32_10((uint32_t)(v + 1), 0u, r_lo, r_hi, k0, k1, nxt);  // next visit's block, off the critical path
+      const uint32_t pos0 = (uint32_t)v * (uint32_t)D;
+      const int el = (int)(pos0 & 3u);
+      if (v > 0 && el == 0) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) blk[w] = nxt[w];
+        philox4x32_10((pos0 >> 2) + 1u, 0u, r_lo, r_hi, k0, k1, nxt);
+      }
       const int cell = visit ? visit[v] : v;
       int c = 0;
+      uint32_t w_ct;
       if (C == 2) {
-        const uint32_t u = bounded_draw(blk, 0, r0 + r1, (uint32_t)v, r_lo, r_hi, k0, k1);
+        const uint32_t w_cd = (el == 0) ? blk[0] : blk[2];  // pos0 is even
+        w_ct = (el == 0) ? blk[1] : blk[3];
+        const uint32_t u = bounded_draw(w_cd, pos0, r0 + r1, r_lo, r_hi, k0, k1);
         c = (u < r0) ? 0 : 1;
         if (c) --r1; else --r0;
+      } else {
+        w_ct = (el == 0) ? blk[0] : (el == 1) ? blk[1] : (el == 2) ? blk[2] : blk[3];
       }
-      uint32_t u = bounded_draw(blk, 1, tot[c], (uint32_t)v, r_lo, r_hi, k0, k1);
+      uint32_t u = bounded_draw(w_ct, pos0 + (uint32_t)(D - 1), tot[c], r_lo, r_hi, k0, k1);
       tot[c] -= 1;
       // level 1: group
       int grp = NG - 1;
@@ -175,8 +182,6 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
       lab2[(size_t)cell * Bpad + off2] = (uint8_t)(c * T + pos);
       if (dbg_ct) dbg_ct[(size_t)q * N + cell] = (uint8_t)pos;
       if (dbg_cond) dbg_cond[(size_t)q * N + cell] = (uint8_t)c;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) blk[w] = nxt[w];
     }
   }
 }

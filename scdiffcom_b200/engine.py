@@ -118,6 +118,11 @@ def device_count() -> int:
     return int(_lib.load().scdc_device_count())
 
 
+def trim(device: int = -1) -> None:
+    """Return the engine's cached device memory (stream-ordered pool) to the driver."""
+    check(_lib.load().scdc_trim(int(device)))
+
+
 def version() -> str:
     return _lib.load().scdc_version().decode()
 
