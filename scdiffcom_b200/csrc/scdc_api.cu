@@ -537,27 +537,28 @@ int scdc_create(const scdc_problem* p, int32_t device, scdc_handle** out) { retu
 namespace {
 
 template <int NG>
-cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int J, uint32_t* bits1,
-                           uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
+cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
+                           uint32_t* bits1, uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
   auto kern = scdc::k_draw_labels<NG>;
   const size_t smem = (size_t)h->C * NG * 8 * 32 * sizeof(uint32_t);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<B / 32, 32, smem, s>>>(h->N, h->T, h->C, h->C == 2 ? h->visit.p : nullptr, h->ct_seg.p, h->expect.p, seed, perm0, B, J,
+  kern<<<B / 32, 32, smem, s>>>(h->N, h->T, h->C, h->C == 2 ? h->visit.p : nullptr, h->ct_seg.p, h->expect.p, seed, perm0, Bb, J,
                                bits1, lab2, dbg_cond, dbg_ct);
   return cudaGetLastError();
 }
 
-cudaError_t launch_draw(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int J, uint32_t* bits1,
-                        uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
+// B = replicates drawn by this launch (a multiple of Bb), Bb = replicates per reduction batch (label block size)
+cudaError_t launch_draw(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
+                        uint32_t* bits1, uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
   const int T = h->T;
-  if (T <= 16) return launch_draw_ng<2>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 32) return launch_draw_ng<4>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 64) return launch_draw_ng<8>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 128) return launch_draw_ng<16>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
-  return launch_draw_ng<32>(h, s, seed, perm0, B, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 16) return launch_draw_ng<2>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 32) return launch_draw_ng<4>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 64) return launch_draw_ng<8>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (T <= 128) return launch_draw_ng<16>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  return launch_draw_ng<32>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
 }
 
 struct ScatterPlan {
@@ -621,8 +622,15 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
   long long B = (long long)(budget / per_perm);
   B = std::min<long long>(B, 4096);
   if (o->batch_size > 0) B = o->batch_size;
-  B = std::min<long long>(B, ((o->iterations + 127) / 128) * 128);
   B = std::max<long long>(128, (B / 128) * 128);
+  if (o->batch_size <= 0) {
+    // equal batches: the reduction always runs whole batches, so ceil(iterations / B) batches of the smallest multiple
+    // of 128 that covers them wastes at most 127 replicates per batch (10 000 -> 3 x 3456 instead of 3 x 4096)
+    const long long nbat = (o->iterations + B - 1) / B;
+    B = std::min<long long>(B, (((o->iterations + nbat - 1) / nbat + 127) / 128) * 128);
+  } else {
+    B = std::min<long long>(B, ((o->iterations + 127) / 128) * 128);
+  }
   return (int)B;
 }
 
@@ -654,7 +662,7 @@ int prelaunch_labels(scdc_handle* h, const scdc_options* o) {
   cudaEventDestroy(dep);
   CU(e1); CU(e2);
   CU(cudaEventRecord(h->pre.t0, h->stream_labels));
-  CU(launch_draw(h, h->stream_labels, o->seed, o->perm_offset, (int)SB, pl.J, h->bits1[0].p, h->lab2[0].p, nullptr, nullptr));
+  CU(launch_draw(h, h->stream_labels, o->seed, o->perm_offset, (int)SB, B, pl.J, h->bits1[0].p, h->lab2[0].p, nullptr, nullptr));
   CU(cudaEventRecord(h->pre.t1, h->stream_labels));
   h->pre.valid = true; h->pre.seed = o->seed; h->pre.perm_offset = o->perm_offset; h->pre.SB = SB; h->pre.J = pl.J;
   return SCDC_OK;
@@ -758,7 +766,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   auto issue_labels = [&](int64_t sb_start, int buf) -> int {
     if (pipelined && freed_set[buf]) CU(cudaStreamWaitEvent(sL, freed[buf], 0));
     CU(mark(evl, sL));
-    CU(launch_draw(h, sL, o->seed, o->perm_offset + sb_start, (int)SB, pl.J, h->bits1[buf].p, h->lab2[buf].p, nullptr, nullptr));
+    CU(launch_draw(h, sL, o->seed, o->perm_offset + sb_start, (int)SB, B, pl.J, h->bits1[buf].p, h->lab2[buf].p, nullptr, nullptr));
     CU(mark(evl, sL));
     if (pipelined) CU(cudaEventRecord(ready[buf], sL));
     ++launches;
@@ -811,8 +819,8 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
         CU(cudaStreamWaitEvent(s, ready[buf], 0));
       }
     }
-    const uint8_t* lab2_b = h->lab2[buf].p + in_sb;            // row stride SB bytes
-    const uint32_t* bits1_b = (C == 2) ? h->bits1[buf].p + in_sb / 32 : nullptr;  // row stride SBw words
+    const uint8_t* lab2_b = h->lab2[buf].p + (size_t)in_sb * N;                      // block [in_sb / B]: [cell][B] bytes
+    const uint32_t* bits1_b = (C == 2) ? h->bits1[buf].p + (size_t)(in_sb / 32) * N : nullptr;  // [cell][B / 32] words
     const int mb = overlap_score ? (int)((done / B) & 1) : 0;  // group-means buffer of this batch
     double* M1b = h->M1[mb].p;
     double* M2b = h->M2[mb].p;
@@ -822,14 +830,14 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       const int nWC = B / 128, W = 8;
       const long long tasks = (long long)h->n_active * nWC;
       scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p,
-                                                                           h->values_s.p, bits1_b, SBw, h->ngroup.p,
+                                                                           h->values_s.p, bits1_b, Bw, h->ngroup.p,
                                                                            h->gene_order.p, M1b);
       CU(cudaGetLastError());
       ++launches; ++reduce_launches;
     }
-    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, (int)SB, M2b, s)
-                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, (int)SB, M2b, s)
-                                   : launch_scatter<1>(h, pl, B, lab2_b, (int)SB, M2b, s);
+    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, B, M2b, s)
+                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, B, M2b, s)
+                                   : launch_scatter<1>(h, pl, B, lab2_b, B, M2b, s);
     CU(le);
     ++launches; ++reduce_launches;
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
@@ -1329,7 +1337,7 @@ int scdc_draw_labels(scdc_handle* h, uint64_t seed, int64_t perm_offset, int64_t
   CU(dcond.alloc((size_t)B * N));
   for (int64_t done = 0; done < n; done += B) {
     const int nb = (int)std::min<int64_t>(B, n - done);
-    CU(launch_draw(h, s, seed, perm_offset + done, B, 1, bits1.p, lab2.p, dcond.p, dct.p));
+    CU(launch_draw(h, s, seed, perm_offset + done, B, B, 1, bits1.p, lab2.p, dcond.p, dct.p));
     CU(cudaMemcpyAsync(ct_out + (size_t)done * N, dct.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));
     if (cond_out && C == 2)
       CU(cudaMemcpyAsync(cond_out + (size_t)done * N, dcond.p, (size_t)nb * N, cudaMemcpyDeviceToHost, s));

@@ -76,18 +76,19 @@ __host__ __device__ inline int lab2_offset(int q, int J) {
 // cell type is two registers; detection: cell order). The cell-type urn is two-level: NG group sums (8 labels per
 // group) in registers, the per-label remaining counts in shared memory laid out [label][thread] (bank = lane).
 // Philox blocks depend only on (seed, replicate, visit), so they are computed off the urn's dependency chain.
-// outputs: bits1[cell][Bpad/32] (bit q%32 of word q/32 = cond' of replicate q), lab2[cell][Bpad] (group code
-// cond' * T + ct' in the K2b layout). Optional replicate-major debug copies for scdc_draw_labels.
+// outputs, per reduction batch of Bb replicates (batch b = q / Bb holds replicates q' = q % Bb):
+//   bits1[b][cell][Bb/32] (bit q'%32 of word q'/32 = cond'), lab2[b][cell][Bb] (group code cond' * T + ct', K2b layout).
+// Batch-major blocks keep the row stride of the labels at Bb bytes however many replicates one launch draws. Optional replicate-major debug copies for scdc_draw_labels.
 // ------------------------------------------------------------------------------------------------------------------
 template <int NG>
 __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const int* __restrict__ visit,
                                                     const int* __restrict__ ct_seg, const uint32_t* __restrict__ ngroup_u,
-                                                    uint64_t seed, int64_t perm0, int Bpad, int J,
+                                                    uint64_t seed, int64_t perm0, int Bb, int J,
                                                     uint32_t* __restrict__ bits1, uint8_t* __restrict__ lab2,
                                                     uint8_t* __restrict__ dbg_cond, uint8_t* __restrict__ dbg_ct) {
   extern __shared__ uint32_t sm_u32[];  // [C][NG*8][32]
   const int tx = threadIdx.x;
-  const int q = blockIdx.x * 32 + tx;  // replicate inside the batch (Bpad % 32 == 0)
+  const int q = blockIdx.x * 32 + tx;  // replicate inside the super-batch (a multiple of 32)
   const uint64_t rep = (uint64_t)(perm0 + q);
   const uint32_t r_lo = (uint32_t)rep, r_hi = (uint32_t)(rep >> 32), k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t gs[2][NG], tot[2] = {0, 0};
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
       tot[c] += sum;
     }
   }
-  const int Bw = Bpad / 32;
-  const int off2 = lab2_offset(q, J);
+  const int Bw = Bb / 32, qb = q % Bb;
+  uint8_t* const lab2_q = lab2 + (size_t)(q / Bb) * N * Bb + lab2_offset(qb, J);
+  uint32_t* const bits1_q = bits1 + (size_t)(q / Bb) * N * Bw + (qb >> 5);
   const int D = C;  // draws per visit
   uint32_t blk[4], nxt[4];
   philox4x32_10(0u, 0u, r_lo, r_hi, k0, k1, blk);
@@ -177,9 +179,9 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
       const int pos = grp * 8 + kk;
       if (C == 2) {
         const uint32_t word = __ballot_sync(0xffffffffu, c == 1);
-        if (tx == 0) bits1[(size_t)cell * Bw + (q >> 5)] = word;
+        if (tx == 0) bits1_q[(size_t)cell * Bw] = word;
       }
-      lab2[(size_t)cell * Bpad + off2] = (uint8_t)(c * T + pos);
+      lab2_q[(size_t)cell * Bb] = (uint8_t)(c * T + pos);
       if (dbg_ct) dbg_ct[(size_t)q * N + cell] = (uint8_t)pos;
       if (dbg_cond) dbg_cond[(size_t)q * N + cell] = (uint8_t)c;
     }
