@@ -242,6 +242,7 @@ int validate_problem(const scdc_problem* p) {
 int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* o) {
   if (!o) return fail(SCDC_EINVAL, "options is NULL");
   if (o->iterations < 1) return fail(SCDC_EINVAL, "iterations must be >= 1");
+  if (o->iterations > 2000000000LL) return fail(SCDC_EINVAL, "iterations must be <= 2e9 per call (32-bit counters)");
   if (o->perm_offset < 0) return fail(SCDC_EINVAL, "perm_offset must be >= 0");
   if (o->score_type != SCDC_SCORE_GEOMETRIC && o->score_type != SCDC_SCORE_ARITHMETIC)
     return fail(SCDC_EINVAL, "unknown score_type %d", o->score_type);
