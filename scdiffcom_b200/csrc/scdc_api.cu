@@ -592,10 +592,10 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
   return pl;
 }
 
-template <int J, int U>
+template <int J, int U, bool PAIR>
 cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
                              double* M2, cudaStream_t s) {
-  auto kern = scdc::k_scatter<J, U>;
+  auto kern = scdc::k_scatter<J, U, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
@@ -611,8 +611,11 @@ cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad
   // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
   const int warps_per_sm = pl.blocks_per_sm * pl.W;
   const int U = env_int("SCDC_U", (J == 1 && warps_per_sm <= 8) ? 16 : 8);
-  if (J == 1 && U == 16) return launch_scatter_u<J, 16>(h, pl, Bpad, lab2, lab_stride, M2, s);
-  return launch_scatter_u<J, 8>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  const int pair = env_int("SCDC_PAIR", (J == 1 && warps_per_sm <= 8) ? 1 : 0);
+  if (J == 1 && U == 16 && pair) return launch_scatter_u<J, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  if (J == 1 && U == 16) return launch_scatter_u<J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  if (J == 1 && pair) return launch_scatter_u<J, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  return launch_scatter_u<J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s);
 }
 
 int pick_batch(const scdc_handle* h, const scdc_options* o) {

@@ -336,7 +336,7 @@ template <> struct LabWord<1> { typedef uint8_t type; };
 template <> struct LabWord<2> { typedef uint16_t type; };
 template <> struct LabWord<4> { typedef uint32_t type; };
 
-template <int J, int U>
+template <int J, int U, bool PAIR>
 __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
                           const double* __restrict__ values, const uint8_t* __restrict__ lab2, int lab_stride,
                           const double* __restrict__ ngroup, const int* __restrict__ gene_order, double* __restrict__ M2) {
@@ -394,13 +394,29 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
         valN[u] = entry_value(en);
         lbN[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en.x * lab_stride);
       }
+      if (PAIR && J == 1) {
+        // Two entries per step: both accumulators are loaded before either add. If the two labels coincide the second
+        // add continues from the first result, so the value stored last is ((acc + v1) + v2): the sequential sum, with a
+        // dependency chain of one shared-memory round trip per PAIR (matters when only ~7 warps are resident, K > 100;
+        // groups of four were measured no faster).
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double cur[J];
+        for (int u = 0; u < U; u += 2) {
+          const int i1 = (int)lb[u] * 32, i2 = (int)lb[u + 1] * 32;
+          const double a1 = acc[i1], a2 = acc[i2];
+          const double r1 = a1 + val[u];
+          const double r2 = ((i1 == i2) ? r1 : a2) + val[u + 1];
+          acc[i1] = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
+          acc[i2] = r2;
+        }
+      } else {
 #pragma unroll
-        for (int j = 0; j < J; ++j) cur[j] = acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32];
+        for (int u = 0; u < U; ++u) {
+          double cur[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val[u];
+          for (int j = 0; j < J; ++j) cur[j] = acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32];
+#pragma unroll
+          for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val[u];
+        }
       }
     }
   }
