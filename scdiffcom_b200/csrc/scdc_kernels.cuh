@@ -627,15 +627,18 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
   __syncthreads();
   const int g_first[2] = {s_gs[0], s_gs[nL]};  // LIGAND_1 / RECEPTOR_1: always present
   const bool has_extra = s_extra != 0;
+  // thread -> (replicate p, cell type ct0 + k * ctstep) without integer divisions (P is a power of two)
+  const int lgP = 31 - __clz(P);
+  const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
   auto issue = [&](int t) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
     double* dst0 = sm_d + (size_t)(t & 1) * NA * tile;
-    for (int item = tid; item < NA * T * P; item += nthr) {
-      const int p = item % P, rest = item / P, ct = rest % T, a = rest / T;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
       const int side = (C == 2) ? ((a >> 1) & 1) : a, cond = (C == 2) ? (a & 1) : 0, pass = (C == 2) ? (a >> 2) : 1;
-      const double* M = pass ? A.M2 : A.M1;
-      cp_async_8(dst0 + a * tile + p * Tp + ct,
-                 M + (((size_t)ch * A.G + g_first[side]) * K + cond * T + ct) * 32 + lane0 + p);
+      const double* src = (pass ? A.M2 : A.M1) + (((size_t)ch * A.G + g_first[side]) * K + cond * T) * 32 + lane0 + p_t;
+      double* dst = dst0 + a * tile + p_t * Tp;
+      for (int ct = ct0; ct < T; ct += ctstep) cp_async_8(dst + ct, src + (size_t)ct * 32);
     }
     cp_async_commit();
   };
@@ -647,8 +650,9 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
     if (C == 2 || has_extra) {
       // ---------------- fix-up: differences of the first subunits, extra subunits folded in ----------------
-      for (int item = tid; item < 2 * T * P; item += nthr) {
-        const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+      for (int side = 0; side < 2; ++side) {
+       for (int ct = ct0; ct < T; ct += ctstep) {
+        const int p = p_t;
         const int s0 = side ? nL : 0, s1 = side ? nS : nL;
         const int o = p * Tp + ct;
         if (C == 2) {
@@ -675,6 +679,7 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
           }
           raw[side * tile + o] = m;
         }
+       }
       }
       __syncthreads();
     }
@@ -872,17 +877,38 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
   __syncthreads();
   const int g_first[2] = {s_gs[0], s_gs[nL]};
   const bool has_extra = s_extra != 0;
+  // thread -> (replicate p, cell type ct0 + k * ctstep) without integer divisions (P is a power of two)
+  const int lgP = 31 - __clz(P);
+  const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
   auto issue = [&](int t) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
     double* dst0 = sm_d + (size_t)(t & 1) * rawSize;
-    for (int item = tid; item < 8 * T * P; item += nthr) {
-      const int p = item % P, rest = item / P, ct = rest % T, rest2 = rest / T, k = rest2 & 3, side = rest2 >> 2;
-      const double* M = (k >> 1) ? A.M2 : A.M1;
-      cp_async_8(dst0 + side * sideStride + (p * Tp + ct) * 4 + k,
-                 M + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T + ct) * 32 + lane0 + p);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double* src = ((k >> 1) ? A.M2 : A.M1) + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T) * 32 + lane0 + p_t;
+        double* dst = dst0 + side * sideStride + p_t * Tp * 4 + k;
+        for (int ct = ct0; ct < T; ct += ctstep) cp_async_8(dst + ct * 4, src + (size_t)ct * 32);
+      }
     }
     cp_async_commit();
   };
+  // FACT: decomposition of this thread's (cell type, subunit) items, once
+  const double* fact_ptr[2] = {nullptr, nullptr};
+  int fact_stride[2] = {0, 0};
+  if (FACT) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int item = tid + w * nthr;
+      if (item < T * nS) {
+        const int ct = item / nS, sx = item % nS;
+        const int nSide = (sx < nL) ? nL : nR;
+        fact_ptr[w] = ((sx < nL) ? DL : DR) + ct * nSide + ((sx < nL) ? sx : sx - nL);
+        fact_stride[w] = Tp * nSide;
+      }
+    }
+  }
   if (n_tiles > 0) issue(0);
   for (int t = 0; t < n_tiles; ++t) {
     if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
@@ -890,8 +916,9 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
     double* raw = sm_d + (size_t)(t & 1) * rawSize;
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
     // ---------------- fix-up: first-subunit differences, extra subunits of complexes folded in ----------------
-    for (int item = tid; item < 2 * T * P; item += nthr) {
-      const int p = item % P, rest = item / P, ct = rest % T, side = rest / T;
+    for (int side = 0; side < 2; ++side) {
+     for (int ct = ct0; ct < T; ct += ctstep) {
+      const int p = p_t;
       const int s0 = side ? nL : 0, nSide = side ? nR : nL;
       double* b4 = raw + side * sideStride + (p * Tp + ct) * 4;  // {pass1 c1, pass1 c2, pass2 c1, pass2 c2}
       double* dd = (side ? DR : DL) + (p * Tp + ct) * nSide;
@@ -909,6 +936,7 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
         dd[k] = d;
       }
       if (has_extra) { b4[0] = m10; b4[1] = m11; b4[2] = m20; b4[3] = m21; }
+     }
     }
     __syncthreads();
     const int pmax = min(P, A.n_valid - pb);
@@ -916,12 +944,9 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
     if (FACT) {
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const int item = tid + w * nthr;
-        if (item < T * nS) {
-          const int ct = item / nS, s = item % nS;
-          const int nSide = (s < nL) ? nL : nR;
-          const double* pd = ((s < nL) ? DL : DR) + ct * nSide + ((s < nL) ? s : s - nL);
-          const int stride = Tp * nSide;
+        if (fact_ptr[w]) {
+          const double* pd = fact_ptr[w];
+          const int stride = fact_stride[w];
           uint32_t c = 0;
           for (int p = 0; p < pmax; ++p) c += (fabs(pd[p * stride]) >= so[w]) ? 1u : 0u;
           sc[w] += c;
