@@ -268,6 +268,8 @@ void scdc_release(scdc_handle* h) {
   cudaSetDevice(h->device);
   cudaStream_t s0 = h->stream, s1 = h->stream_labels, s2 = h->stream_score;
   cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1;
+  if (s1) cudaStreamSynchronize(s1);  // e.g. labels drawn ahead of a run that never happened
+  if (s2) cudaStreamSynchronize(s2);
   {
     AllocScope scope(s0);
     if (!s0) g_alloc_async = false;
