@@ -91,7 +91,10 @@ class ClockSampler:
 def build_workload(name):
     from scdiffcom_b200 import synthetic
     cfg = dict(synthetic.CONFIGS[name])
-    prob, ai, simple, mask = synthetic.make_problem(name)
+    lri = None
+    if name == "config4":   # BASELINE.json config 4 uses the real LRI_human table (decoded fixture, tests/golden/)
+        lri = dict(np.load(os.path.join(ROOT, "tests", "golden", "LRI_human_curated.npz")))
+    prob, ai, simple, mask = synthetic.make_problem(name, lri_table=lri)
     return prob, cfg
 
 

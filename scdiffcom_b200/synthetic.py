@@ -48,9 +48,17 @@ def synthetic_lri_table(n_lri, genes, rng):
 
 
 def make_analysis_inputs(n_cells, n_genes, n_celltypes, n_conditions, n_lri, seed, min_group=50, iterations=None,
-                         density_scale=1.0):
-    """Returns the `analysis_inputs` dict (same keys as preprocessing.extract_analysis_inputs)."""
+                         density_scale=1.0, lri_table=None):
+    """Returns the `analysis_inputs` dict (same keys as preprocessing.extract_analysis_inputs).
+    lri_table: optional real LRI table (dict with LRI, LIGAND_1..2, RECEPTOR_1..3 columns, "" = NA); the matrix genes are
+    then named after its gene symbols (BASELINE.json config 4: LRI_human) and n_genes / n_lri are taken from it."""
     rng = np.random.default_rng(seed)
+    real_genes = None
+    if lri_table is not None:
+        cols = ("LIGAND_1", "LIGAND_2", "RECEPTOR_1", "RECEPTOR_2", "RECEPTOR_3")
+        real_genes = np.unique(np.concatenate([np.asarray(lri_table[c]) for c in cols]))
+        real_genes = real_genes[real_genes != ""]
+        n_genes = len(real_genes)
     N, G, T, C = n_cells, n_genes, n_celltypes, n_conditions
     floor = min_group * C + 20 * C
     if floor * T > N:
@@ -87,8 +95,15 @@ def make_analysis_inputs(n_cells, n_genes, n_celltypes, n_conditions, n_lri, see
     if indptr[-1] >= 2**31:
         raise ValueError("nnz exceeds int32 (dgCMatrix limit)")
     data_tr = sp.csc_matrix((np.concatenate(val_chunks), np.concatenate(idx_chunks), indptr.astype(np.int32)), shape=(N, G))
-    genes = np.array([f"G{g:05d}" for g in range(G)])
-    LRI = synthetic_lri_table(n_lri, genes, rng)
+    if real_genes is not None:
+        genes = real_genes
+        table = np.stack([np.asarray(lri_table[c], dtype=np.str_) for c in ("LRI", "LIGAND_1", "LIGAND_2", "RECEPTOR_1", "RECEPTOR_2", "RECEPTOR_3")], axis=1)
+        _, first = np.unique(table, axis=0, return_index=True)
+        table = table[np.sort(first)]
+        LRI = {c: table[:, k] for k, c in enumerate(("LRI", "LIGAND_1", "LIGAND_2", "RECEPTOR_1", "RECEPTOR_2", "RECEPTOR_3"))}
+    else:
+        genes = np.array([f"G{g:05d}" for g in range(G)])
+        LRI = synthetic_lri_table(n_lri, genes, rng)
     max_nL = 2 if np.any(LRI["LIGAND_2"] != "") else 1
     max_nR = 3 if np.any(LRI["RECEPTOR_3"] != "") else (2 if np.any(LRI["RECEPTOR_2"] != "") else 1)
     for c in ["LIGAND_2"] * (max_nL < 2) + ["RECEPTOR_3"] * (max_nR < 3) + ["RECEPTOR_2"] * (max_nR < 2):
@@ -103,12 +118,12 @@ def make_analysis_inputs(n_cells, n_genes, n_celltypes, n_conditions, n_lri, see
             "max_nL": max_nL, "max_nR": max_nR, "condition": cond}
 
 
-def make_problem(name_or_kwargs, score_type="geometric_mean"):
+def make_problem(name_or_kwargs, score_type="geometric_mean", lri_table=None):
     """Synthetic inputs -> observed pass -> (PermutationProblem, analysis_inputs, cci_dt_simple, tested mask)."""
     from . import cci, permutation
     kw = dict(CONFIGS[name_or_kwargs]) if isinstance(name_or_kwargs, str) else dict(name_or_kwargs)
     kw.pop("iterations", None)
-    ai = make_analysis_inputs(**kw)
+    ai = make_analysis_inputs(lri_table=lri_table, **kw)
     tmpl = cci.create_cci_template(ai)
     simple = cci.run_simple_cci_analysis(ai, tmpl, score_type=score_type)
     prob, mask = permutation.build_problem(ai, simple)

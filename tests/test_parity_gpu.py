@@ -232,3 +232,34 @@ def test_observed_pass_on_gpu_and_one_resident_engine(liver, mode, score_type):
     for name in b["cci_raw"]:
         if "P_VALUE" in name:
             assert np.array_equal(a["cci_raw"][name], b["cci_raw"][name], equal_nan=True), name
+
+
+@pytest.mark.parametrize("name", ["config2", "config3"])
+def test_full_size_identity_labels_reproduce_the_observed_pass(name):
+    """BASELINE.json's full-size synthetic configs through a size-independent property: uploading the ORIGINAL labels as
+    every replicate must reproduce the observed scores exactly, and `>=` counts ties, so every counter equals the number of
+    replicates (NaN where the subunit is NA). Observed values come from the GPU observed pass on the same engine."""
+    from scdiffcom_b200 import cci
+    from scdiffcom_b200 import permutation as perm
+    kw = dict(synthetic.CONFIGS[name]); kw.pop("iterations")
+    ai = synthetic.make_analysis_inputs(**kw)
+    tmpl = cci.create_cci_template(ai)
+    n = 128
+    with Engine(cci.base_problem(ai)) as eng:
+        simple = cci.run_simple_cci_analysis(ai, tmpl, engine=eng)
+        mask, r_lri, r_emit, r_recv, obs = perm.tested_row_arrays(ai, simple)
+        eng.set_rows(r_lri, r_emit, r_recv, obs)
+        pr = eng.problem
+        pct = np.tile(np.asarray(pr.ct_code, dtype=np.uint8), (n, 1))
+        pcond = np.tile(np.asarray(pr.cond_code, dtype=np.uint8), (n, 1)) if pr.n_conditions == 2 else None
+        got = eng.run(n, perm_cond=pcond, perm_ct=pct)["counts"]
+        # device-drawn replicates: every counter stays within [0, n] and the run is deterministic
+        a = eng.run(n, seed=3)["counts"]
+        b = eng.run(n, seed=3)["counts"]
+    expect = np.where(np.isnan(obs), np.nan, float(n))
+    assert got.shape == expect.shape and got.shape[0] > 200_000
+    assert np.array_equal(got, expect, equal_nan=True)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert np.nanmax(a) <= n and np.nanmin(a) >= 0
+    zero_obs = obs[:, -1 if pr.n_conditions == 1 else 2] == 0          # observed score 0: every replicate counts
+    assert np.all(a[zero_obs, -1 if pr.n_conditions == 1 else 2] == n)
