@@ -857,26 +857,20 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(mark(evk, sS));
     }
     if (R > 0 && !dist_host && !env_int("SCDC_SCORE_V1", 0)) {
-      scdc::ScoreV2Args A;
-      A.G = G; A.T = T; A.Tp = T | 1; A.K = K; A.nL = h->nL; A.nS = h->nS; A.ncols = h->ncols; A.score_type = o->score_type;
-      A.nChunks = (nb + 31) / 32; A.n_valid = nb; A.R = R;
+      const int Tp = T | 1;
       const int n_arr = (C == 2) ? 16 + h->nS : 4;  // RAW tiles double-buffered (2 x 8 | 2 x 2) + D tiles
       int P = 32;
       const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", 100) * 1024;
-      while (P > 4 && (size_t)n_arr * P * A.Tp * 8 > smem_target) P >>= 1;
+      while (P > 4 && (size_t)n_arr * P * Tp * 8 > smem_target) P >>= 1;
       P = env_int("SCDC_SCORE_P", P);
-      A.P = P;
-      const size_t smem = (size_t)n_arr * P * A.Tp * 8;
-      A.task_lri = h->task_lri.p; A.task_beg = h->task_beg.p; A.task_end = h->task_end.p; A.srow = h->srow.p;
-      A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p; A.thr = h->thr.p;
-      A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p;
+      const size_t smem = (size_t)n_arr * P * Tp * 8;
       if (C == 2) {
         scdc::ScoreDiffArgs D;
-        D.G = G; D.T = T; D.Tp = A.Tp; D.K = K; D.nL = h->nL; D.nR = h->nR; D.score_type = o->score_type;
+        D.G = G; D.T = T; D.Tp = Tp; D.K = K; D.nL = h->nL; D.nR = h->nR; D.score_type = o->score_type;
         D.n_valid = nb; D.P = P; D.R = R;
-        D.task_lri = A.task_lri; D.task_beg = A.task_beg; D.task_end = A.task_end; D.srow = A.srow;
-        D.sub_gene = A.sub_gene; D.row_emit = A.row_emit; D.row_recv = A.row_recv; D.obs = A.obs; D.thr = A.thr;
-        D.obs_sub = h->obs_sub.p; D.M1 = M1b; D.M2 = M2b; D.counts = h->counts.p;
+        D.task_lri = h->task_lri.p; D.task_beg = h->task_beg.p; D.task_end = h->task_end.p; D.srow = h->srow.p;
+        D.sub_gene = h->sub_gene.p; D.row_emit = h->row_emit.p; D.row_recv = h->row_recv.p; D.obs = h->obs.p;
+        D.thr = h->thr.p; D.obs_sub = h->obs_sub.p; D.M1 = M1b; D.M2 = M2b; D.counts = h->counts.p;
         if (h->fact_ok) {
           auto kern = scdc::k_score_diff<kScoreRPT, true>;
           CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -887,7 +881,13 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
           kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
         }
       } else {
-        auto kern = scdc::k_score_v2<1, kScoreRPT>;
+        scdc::ScoreDetArgs A;
+        A.G = G; A.T = T; A.Tp = Tp; A.nL = h->nL; A.nS = h->nS; A.score_type = o->score_type;
+        A.n_valid = nb; A.P = P; A.R = R;
+        A.task_lri = h->task_lri.p; A.task_beg = h->task_beg.p; A.task_end = h->task_end.p; A.srow = h->srow.p;
+        A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p;
+        A.thr = h->thr.p; A.M2 = M2b; A.counts = h->counts.p;
+        auto kern = scdc::k_score_det<kScoreRPT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
       }

@@ -542,35 +542,19 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K3 (v2, the production path): factorised per LRI. A block owns one LRI and a slice of its tested rows (thread = row,
-// RPT rows per thread, counters and observed values in registers for the whole launch) and walks the batch P replicates
+// K3 (production path): factorised per LRI. A block owns one LRI and a slice of its tested rows (thread = row, RPT rows
+// per thread; observed values, thresholds and counters in registers for the whole launch) and walks the batch P replicates
 // at a time:
-//   stage A: min over the LRI's present ligand subunits per (condition, cell type) and the same for the receptor side
-//            (pmin(na.rm = TRUE), reference R/utils_cci.R:613-653), plus the per-subunit cond2 - cond1 differences, go to
-//            shared memory as [replicate][cell type] tiles (cp.async double-buffered, one tile ahead);
-//   stage B: every row combines its emitter / receiver entries: score, DE difference, `>=` compares, register counters.
-// No ballots, no atomics, no re-reading of the means per row. The one-sided geometric columns compare the PRODUCT with a
-// host-precomputed threshold thr = min{y : sqrt_rn(y) >= observed}; sqrt_rn is monotone, so
-// (sqrt(a*b) >= observed) == (a*b >= thr) exactly and the fp64 sqrt disappears from those columns.
+//   tiles   : min over the LRI's present ligand subunits per cell type and the same for the receptor side
+//             (pmin(na.rm = TRUE), reference R/utils_cci.R:613-653) in shared memory as [replicate][cell type] tiles, filled
+//             by cp.async (LDGSTS) ONE TILE AHEAD of their use (double-buffered), so the global-memory latency hides behind
+//             the row work of the previous tile; a fix-up pass folds the extra subunits of complexes in (rare);
+//   rows    : every row combines its emitter / receiver entries: score, `>=` compare, register counter.
+// No ballots, no atomics, no re-reading of the means per row. The one-sided geometric columns compare the PRODUCT with
+// thr = min{y : sqrt_rn(y) >= observed} (k_product_thresholds); sqrt_rn is monotone, so
+// (sqrt(a*b) >= observed) == (a*b >= thr) exactly and the fp64 sqrt disappears.
+// k_score_det: detection mode (one column). k_score_diff (below): differential mode (3 + nL + nR columns).
 // ------------------------------------------------------------------------------------------------------------------
-struct ScoreV2Args {
-  int G, T, Tp, K, nL, nS, ncols, score_type;
-  int nChunks, n_valid, P;
-  int R;
-  const int* task_lri;
-  const int* task_beg;
-  const int* task_end;
-  const int* srow;      // [R] original row id of each LRI-sorted position
-  const int* sub_gene;
-  const int* row_emit;
-  const int* row_recv;
-  const double* obs;    // column-major [R][ncols], original row ids
-  const double* thr;    // column-major [R][C] product thresholds (geometric one-sided columns), original row ids
-  const double* M1;
-  const double* M2;
-  uint32_t* counts;
-};
-
 __device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -579,19 +563,32 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Shared-memory plan: RAW[2 buffers][NA arrays][P][Tp] + D[nS][P][Tp] (differential only), NA = 8 (array = pass*4 + side*2
-// + cond) or 2 (array = side). RAW tiles are filled by cp.async (LDGSTS) one tile ahead of their use, so the global-memory
-// latency of stage A is hidden behind stage B of the previous tile; the fix-up pass (first-subunit differences, extra
-// subunits of complexes folded in with fmin) works shared-to-shared except for the (rare) extra subunits.
-template <int C, int RPT>
-__global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
+struct ScoreDetArgs {
+  int G, T, Tp, nL, nS, score_type;
+  int n_valid, P;
+  int R;
+  const int* task_lri;
+  const int* task_beg;
+  const int* task_end;
+  const int* srow;      // [R] original row id of each LRI-sorted position
+  const int* sub_gene;
+  const int* row_emit;
+  const int* row_recv;
+  const double* obs;    // [R] observed CCI_SCORE, original row ids
+  const double* thr;    // [R] product thresholds (geometric score)
+  const double* M2;     // group means [chunk32][gene][T][32]
+  uint32_t* counts;     // [R]
+};
+
+// shared memory: RAW[2 buffers][2 sides][P][Tp] doubles
+template <int RPT>
+__global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
   extern __shared__ __align__(16) double sm_d[];
   __shared__ int s_gs[8];
   __shared__ int s_extra;
-  constexpr int NA = (C == 2) ? 8 : 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
-  const int T = A.T, Tp = A.Tp, P = A.P, K = A.K, nL = A.nL, nS = A.nS;
+  const int T = A.T, Tp = A.Tp, P = A.P, nL = A.nL, nS = A.nS;
   if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
   if (tid == 0) {
     int extra = 0;
@@ -599,45 +596,38 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
       if (s != 0 && s != nL && A.sub_gene[l * nS + s] >= 0) extra = 1;
     s_extra = extra;
   }
-  constexpr int NOB = (C == 2) ? 11 : 1;
   int e_[RPT], r_[RPT], rid[RPT];
-  double ob[RPT][NOB], th[RPT][2];
-  uint32_t cnt[RPT][NOB];
+  double ob[RPT], th[RPT];
+  uint32_t cnt[RPT];
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     const int pos = rb + tid + q * nthr;
     rid[q] = (pos < re) ? A.srow[pos] : -1;
     e_[q] = r_[q] = 0;
-#pragma unroll
-    for (int c = 0; c < NOB; ++c) { ob[q][c] = 0.0; cnt[q][c] = 0; }
-    th[q][0] = th[q][1] = 0.0;
+    ob[q] = th[q] = 0.0;
+    cnt[q] = 0;
     if (rid[q] >= 0) {
       e_[q] = A.row_emit[rid[q]];
       r_[q] = A.row_recv[rid[q]];
-#pragma unroll
-      for (int c = 0; c < NOB; ++c)
-        if (c < A.ncols) ob[q][c] = A.obs[(size_t)c * A.R + rid[q]];
-      th[q][0] = A.thr[rid[q]];
-      if (C == 2) th[q][1] = A.thr[(size_t)A.R + rid[q]];
+      ob[q] = A.obs[rid[q]];
+      th[q] = A.thr[rid[q]];
     }
   }
-  const int tile = P * Tp;  // doubles per staged array
-  double* const Dbase = sm_d + 2 * NA * tile;
+  const int tile = P * Tp;  // doubles per (buffer, side)
   const int n_tiles = (A.n_valid + P - 1) / P;
   __syncthreads();
   const int g_first[2] = {s_gs[0], s_gs[nL]};  // LIGAND_1 / RECEPTOR_1: always present
   const bool has_extra = s_extra != 0;
-  // thread -> (replicate p, cell type ct0 + k * ctstep) without integer divisions (P is a power of two)
+  // thread -> (replicate p_t, cell type ct0 + k * ctstep) without integer divisions (P is a power of two)
   const int lgP = 31 - __clz(P);
   const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
   auto issue = [&](int t) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    double* dst0 = sm_d + (size_t)(t & 1) * NA * tile;
+    double* dst0 = sm_d + (size_t)(t & 1) * 2 * tile;
 #pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const int side = (C == 2) ? ((a >> 1) & 1) : a, cond = (C == 2) ? (a & 1) : 0, pass = (C == 2) ? (a >> 2) : 1;
-      const double* src = (pass ? A.M2 : A.M1) + (((size_t)ch * A.G + g_first[side]) * K + cond * T) * 32 + lane0 + p_t;
-      double* dst = dst0 + a * tile + p_t * Tp;
+    for (int side = 0; side < 2; ++side) {
+      const double* src = A.M2 + (((size_t)ch * A.G + g_first[side]) * T) * 32 + lane0 + p_t;
+      double* dst = dst0 + side * tile + p_t * Tp;
       for (int ct = ct0; ct < T; ct += ctstep) cp_async_8(dst + ct, src + (size_t)ct * 32);
     }
     cp_async_commit();
@@ -646,101 +636,47 @@ __global__ void __launch_bounds__(256, 2) k_score_v2(ScoreV2Args A) {
   for (int t = 0; t < n_tiles; ++t) {
     if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();  // tile t is in shared memory for every thread
-    double* raw = sm_d + (size_t)(t & 1) * NA * tile;
+    double* raw = sm_d + (size_t)(t & 1) * 2 * tile;
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    if (C == 2 || has_extra) {
-      // ---------------- fix-up: differences of the first subunits, extra subunits folded in ----------------
+    if (has_extra) {  // complexes: fold the extra subunits in
       for (int side = 0; side < 2; ++side) {
-       for (int ct = ct0; ct < T; ct += ctstep) {
-        const int p = p_t;
         const int s0 = side ? nL : 0, s1 = side ? nS : nL;
-        const int o = p * Tp + ct;
-        if (C == 2) {
-          double* b1 = raw + side * 2 * tile + o;  // pass 1: [0] cond1, [tile] cond2 ; pass 2: [4 tile], [5 tile]
-          double m10 = b1[0], m11 = b1[tile], m20 = b1[4 * tile], m21 = b1[5 * tile];
-          Dbase[s0 * tile + o] = m11 - m10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
+        for (int ct = ct0; ct < T; ct += ctstep) {
+          double m = raw[side * tile + p_t * Tp + ct];
           for (int s = s0 + 1; s < s1; ++s) {
             const int g = s_gs[s];
-            double d = 0.0;
-            if (g >= 0) {
-              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
-              const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
-              d = a11 - a10;
-              m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
-            }
-            Dbase[s * tile + o] = d;
+            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * T + ct) * 32 + lane0 + p_t]);
           }
-          if (has_extra) { b1[0] = m10; b1[tile] = m11; b1[4 * tile] = m20; b1[5 * tile] = m21; }
-        } else {
-          double m = raw[side * tile + o];
-          for (int s = s0 + 1; s < s1; ++s) {
-            const int g = s_gs[s];
-            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p]);
-          }
-          raw[side * tile + o] = m;
+          raw[side * tile + p_t * Tp + ct] = m;
         }
-       }
       }
       __syncthreads();
     }
-    // ---------------- stage B ----------------
     const int pmax = min(P, A.n_valid - pb);
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (rid[q] < 0) continue;
-      const int e = e_[q], r = r_[q];
-      if (C == 1) {
-        const double* pa = raw + e;
-        const double* pbp = raw + tile + r;
-        if (A.score_type == 0) {
+      const double* pa = raw + e_[q];
+      const double* pbp = raw + tile + r_[q];
+      uint32_t c = 0;
+      if (A.score_type == 0) {
 #pragma unroll 4
-          for (int p = 0; p < pmax; ++p) cnt[q][0] += (pa[p * Tp] * pbp[p * Tp] >= th[q][0]) ? 1u : 0u;
-        } else {
-#pragma unroll 4
-          for (int p = 0; p < pmax; ++p) cnt[q][0] += ((pa[p * Tp] + pbp[p * Tp]) / 2 >= ob[q][0]) ? 1u : 0u;
-        }
+        for (int p = 0; p < pmax; ++p) c += (pa[p * Tp] * pbp[p * Tp] >= th[q]) ? 1u : 0u;
       } else {
-        const double aob0 = fabs(ob[q][0]);
-#pragma unroll 2
-        for (int p = 0; p < pmax; ++p) {
-          const double* pa = raw + p * Tp + e;             // ligand side arrays 0,1 (pass 1), 4,5 (pass 2)
-          const double* pbp = raw + 2 * tile + p * Tp + r;  // receptor side arrays 2,3 (pass 1), 6,7 (pass 2)
-          const double a10 = pa[0], a11 = pa[tile], a20 = pa[4 * tile], a21 = pa[5 * tile];
-          const double b10 = pbp[0], b11 = pbp[tile], b20 = pbp[4 * tile], b21 = pbp[5 * tile];
-          double de;
-          if (A.score_type == 0) {
-            de = sqrt(a11 * b11) - sqrt(a10 * b10);
-            cnt[q][1] += (a20 * b20 >= th[q][0]) ? 1u : 0u;
-            cnt[q][2] += (a21 * b21 >= th[q][1]) ? 1u : 0u;
-          } else {
-            de = (a11 + b11) / 2 - (a10 + b10) / 2;
-            cnt[q][1] += ((a20 + b20) / 2 >= ob[q][1]) ? 1u : 0u;
-            cnt[q][2] += ((a21 + b21) / 2 >= ob[q][2]) ? 1u : 0u;
-          }
-          cnt[q][0] += (fabs(de) >= aob0) ? 1u : 0u;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            if (s < nS) {
-              const double d = Dbase[s * tile + p * Tp + (s < nL ? e : r)];
-              cnt[q][3 + s] += (fabs(d) >= fabs(ob[q][3 + s])) ? 1u : 0u;
-            }
-          }
-        }
+#pragma unroll 4
+        for (int p = 0; p < pmax; ++p) c += ((pa[p * Tp] + pbp[p * Tp]) / 2 >= ob[q]) ? 1u : 0u;
       }
+      cnt[q] += c;
     }
-    __syncthreads();  // everyone is done with buffer t & 1 and D before they are overwritten
+    __syncthreads();  // everyone is done with buffer t & 1 before it is overwritten
   }
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    if (rid[q] < 0) continue;
-#pragma unroll
-    for (int c = 0; c < NOB; ++c)
-      if (c < A.ncols) A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
-  }
+  for (int q = 0; q < RPT; ++q)
+    if (rid[q] >= 0) A.counts[rid[q]] += cnt[q];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K3, differential mode (production): same block / tile structure as k_score_v2, tuned for the 3 + nL + nR columns.
+// K3, differential mode (production): same block / tile structure as k_score_det, for the 3 + nL + nR columns.
 //   * tiles are interleaved [side][replicate][cell type][pass*2 + cond]: a row reads its emitter's four ligand minima
 //     and its receiver's four receptor minima with two 16-byte loads each and no per-access index arithmetic;
 //   * FACT: the per-subunit columns |L_i / R_j cond2 - cond1| >= |observed| depend only on (LRI, emitter) resp.
