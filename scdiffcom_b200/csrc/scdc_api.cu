@@ -478,13 +478,14 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     h->gene_nnz_h.resize(G);
     for (int g = 0; g < G; ++g) h->gene_nnz_h[g] = p->colptr[g + 1] - p->colptr[g];
     pt.lap("create: enqueue uploads");
-    std::vector<int> segptr, rows_s;
-    std::vector<double> vals_s;
+    std::vector<int> segptr;
+    std::unique_ptr<int[]> rows_s;        // not value-initialised: the worker threads first-touch their own ranges
+    std::unique_ptr<double[]> vals_s;
     if (C == 2) {
       // pass-1 copy of the matrix: inside each gene column, entries stably sorted by cell type
       segptr.resize((size_t)G * (T + 1));
-      rows_s.resize(h->nnz);
-      vals_s.resize(h->nnz);
+      rows_s.reset(new int[h->nnz ? h->nnz : 1]);
+      vals_s.reset(new double[h->nnz ? h->nnz : 1]);
       // host threads over contiguous gene ranges of about equal nnz (the counting sort is O(nnz) with random ct lookups)
       const int n_thr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
       std::vector<std::thread> workers;
@@ -514,8 +515,9 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       }
       for (auto& t : workers) t.join();
       CU(h->segptr.upload(segptr.data(), segptr.size(), s));
-      CU(h->rowidx_s.upload(rows_s.data(), h->nnz, s));
-      CU(h->values_s.upload(vals_s.data(), h->nnz, s));
+      pt.lap("create: pass-1 copy built");
+      CU(h->rowidx_s.upload(rows_s.get(), h->nnz, s));
+      CU(h->values_s.upload(vals_s.get(), h->nnz, s));
     }
     // K3 v2 work list: rows stably sorted by LRI, each LRI cut into slices of kScoreThreads * kScoreRPT rows
     pt.lap("create: pass-1 matrix copy");
