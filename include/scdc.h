@@ -115,6 +115,8 @@ typedef struct scdc_stats {
   double ms_merge;      /* counter merge across GPUs + D2H */
   double ms_device;     /* device time of the whole batch loop, first to last CUDA event (max over GPUs) */
   double reduce_bytes;  /* algorithmic bytes of all group-sum launches ("algorithmic bytes") */
+  double reduce_wavefronts; /* shared-memory wavefronts the group-sum kernels must issue by design: the unit
+                           that actually bounds them (one wavefront per clock per SM) */
   int64_t reduce_launches;
   int64_t kernel_launches; /* all kernels launched by the call */
   int64_t batch_size;   /* replicates per launch actually used */

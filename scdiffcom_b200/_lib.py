@@ -51,6 +51,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("ms_total", C.c_double), ("ms_upload", C.c_double), ("ms_labels", C.c_double), ("ms_reduce", C.c_double),
         ("ms_score", C.c_double), ("ms_merge", C.c_double), ("ms_device", C.c_double), ("reduce_bytes", C.c_double),
+        ("reduce_wavefronts", C.c_double),
         ("reduce_launches", C.c_int64), ("kernel_launches", C.c_int64), ("batch_size", C.c_int64),
         ("n_gpus", C.c_int32), ("reserved", C.c_int32),
     ]

@@ -768,7 +768,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     }
   }
   int64_t launches = 0, reduce_launches = 0;
-  double reduce_bytes = 0;
+  double reduce_bytes = 0, reduce_wavefronts = 0;
   const double sv = 8.0;
   CU(mark(evs, s));  // evs[0]: start of the whole loop on the compute stream
   auto issue_labels = [&](int64_t sb_start, int buf) -> int {
@@ -852,6 +852,10 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
                     (double)B * N * (C == 2 ? 1.125 : 1.0) + (double)C * B * K * h->n_active * sv;
+    // shared-memory wavefronts by design: per (entry x 32J replicates) the scatter issues a 2-wavefront entry broadcast,
+    // J x (LDS.64 + STS.64) = 4J and 4/32 for the staging store; pass 1 only the broadcast and the staging store
+    reduce_wavefronts += (double)h->nnz_active * (B / (32.0 * pl.J)) * (2.0 + 4.0 * pl.J + 0.125) +
+                         (C == 2 ? (double)h->nnz_active * (B / 128.0) * 2.125 : 0.0);
     CU(mark(evs, s));
     if (overlap_score) {
       CU(cudaEventRecord(m_ready[mb], s));
@@ -959,6 +963,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       st->ms_device += d;
     }
     st->reduce_bytes += reduce_bytes;
+    st->reduce_wavefronts += reduce_wavefronts;
     st->reduce_launches += reduce_launches;
     st->kernel_launches += launches;
     st->batch_size = B;
@@ -1179,6 +1184,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     res->stats.ms_device = std::max(res->stats.ms_device, sts[r].ms_device);
     res->stats.ms_upload = std::max(res->stats.ms_upload, hs[r]->ms_upload);
     res->stats.reduce_bytes += sts[r].reduce_bytes;
+    res->stats.reduce_wavefronts += sts[r].reduce_wavefronts;
     res->stats.reduce_launches += sts[r].reduce_launches;
     res->stats.kernel_launches += sts[r].kernel_launches + 1;
     res->stats.batch_size = sts[r].batch_size;
