@@ -203,7 +203,7 @@ struct scdc_handle {
   DBuf<uint32_t> expect;      // n(cell type, condition) as uint32 [K]
   DBuf<int> visit, ct_seg;     // K1 visit order (differential: cells stably sorted by cell type) and its segments
   std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
-  // K3 v2: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
+  // K3: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
   DBuf<double> thr, obs_sub;   // obs_sub: [L][T][nS] common observed subunit differences (factorised subunit columns)
   bool fact_ok = false;
@@ -599,7 +599,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       CU(upload_big(h->rowidx_s, rows_s.get(), h->nnz, s));
       CU(upload_big(h->values_s, vals_s.get(), h->nnz, s));
     }
-    // K3 v2 work list: rows stably sorted by LRI, each LRI cut into slices of kScoreThreads * kScoreRPT rows
     pt.lap("create: pass-1 matrix copy");
     rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
     if (rc) return rc;

@@ -1,14 +1,19 @@
 // scdc_kernels.cuh — sm_100a kernels of the permutation-test hot path (see DESIGN.md for the data layout).
 //
-//   K1  k_draw_labels      on-device Philox4x32-10 label shuffles          (replaces base::sample at
-//                                                                            reference R/utils_permutation.R:509,536-541,552-569)
-//   K1u k_pack_uploaded    validation mode: re-layout uploaded label matrices
-//   K2a k_pass1_cond       differential pass 1 (conditions shuffled inside fixed cell types): register accumulators
-//   K2b k_scatter<J>       general segmented sum over CSC, lane = replicate, shared-memory accumulators
-//                          (replaces DelayedArray::rowsum + "/ table(group)", reference R/utils_cci.R:441-462)
-//   K3  k_score_count      gather + complex-min + score + diff + `>=` compare + counter bump
-//                          (replaces build_cci_or_drate("cci"), reference R/utils_cci.R:464-712, the column assembly
-//                          of R/utils_permutation.R:579-602 and the counting of R/utils_permutation.R:139-211)
+//   K1   k_draw_labels<NG>   on-device Philox4x32-10 label shuffles (sequential urn draws, one thread per replicate)
+//                             (replaces base::sample at reference R/utils_permutation.R:509,536-541,552-569)
+//   K1u  k_pack_uploaded /    validation mode: re-layout and check uploaded label matrices
+//        k_check_uploaded
+//   K2a  k_pass1_cond         differential pass 1 (conditions shuffled inside fixed cell types): register accumulators
+//   K2b  k_scatter<J,U,PAIR>  general segmented sum over CSC, lane = replicate, shared-memory accumulators
+//                             (replaces DelayedArray::rowsum + "/ table(group)", reference R/utils_cci.R:441-462)
+//   K3   k_score_det /        gather + complex-min + score + diff + `>=` compare + counter bump, factorised per LRI
+//        k_score_diff         (replaces build_cci_or_drate("cci"), reference R/utils_cci.R:464-712, the column assembly
+//                             of R/utils_permutation.R:579-602 and the counting of R/utils_permutation.R:139-211)
+//        k_score_count        generic warp-per-row variant (return_distributions, cross-check)
+//        k_product_thresholds thresholds on the product for the one-sided geometric columns
+//   obs  k_group_means /      observed pass on the original labels (reference R/utils_cci.R:171-283)
+//        k_observed_rows
 //
 // Exactness contract: every (gene, group) sum is accumulated in fp64 by ONE lane walking the gene column in ascending
 // cell order — the order of the C loop behind rowsum — so means, scores and therefore exceedance counts are bit-identical
