@@ -33,6 +33,26 @@ def test_liver_uploaded_labels_bit_exact(liver, mode, score_type):
     assert got["stats"]["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("mode", ["cond", "nocond"])
+def test_distributions_across_several_batches(liver_cases, mode):
+    """return_distributions with more replicates than one device batch: every batch lands at its own offset."""
+    prob = liver_cases[mode]["prob"]
+    pcond, pct = helpers.reference_like_labels(prob, 300, 21)
+    want, want_d = oracle_c.perm_counts(prob, pct, pcond, return_distributions=True)
+    got = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, batch_size=128, return_distributions=True)
+    assert np.array_equal(got["counts"], want, equal_nan=True)
+    assert np.array_equal(got["distributions"], want_d)
+    # device-drawn labels: distributions and counts of the same call are consistent with each other
+    dev = perm_counts(prob, 300, seed=8, batch_size=128, return_distributions=True)
+    d, obs = dev["distributions"], np.asarray(prob.observed).reshape(prob.n_rows, prob.ncols)
+    if mode == "nocond":
+        assert np.array_equal((d[:, 0, :] >= obs[:, 0]).sum(0), dev["counts"][:, 0])
+    else:
+        assert np.array_equal((np.abs(d[:, 0, :]) >= np.abs(obs[:, 0])).sum(0), dev["counts"][:, 0])
+        assert np.array_equal((d[:, 1, :] >= obs[:, 1]).sum(0), dev["counts"][:, 1])
+        assert np.array_equal((d[:, 2, :] >= obs[:, 2]).sum(0), dev["counts"][:, 2])
+
+
 def test_liver_counts_do_not_depend_on_batch_size(liver_cases):
     prob = liver_cases["cond"]["prob"]
     pcond, pct = helpers.reference_like_labels(prob, 300, 9)
