@@ -11,56 +11,8 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 
 
-def random_problem(seed, C, N, G, T, L, nL, nR, R, empty_cols=True):
-    rng = np.random.default_rng(seed)
-    # labels: every (cond, ct) group non-empty
-    base = np.arange(C * T).repeat(2)
-    grp = np.concatenate([base, rng.integers(0, C * T, size=N - len(base))])
-    grp = rng.permutation(grp)
-    ct, cond = (grp % T).astype(np.int32), (grp // T).astype(np.int32)
-    cols, idx, val = [0], [], []
-    for g in range(G):
-        d = 0.0 if (empty_cols and g % 5 == 4) else rng.uniform(0.05, 0.9)
-        nz = np.flatnonzero(rng.random(N) < d)
-        idx.append(nz)
-        v = np.exp(rng.normal(0, 2, size=len(nz)))
-        v[rng.random(len(nz)) < 0.1] = 1.0         # repeated values -> exact ties between group sums are possible
-        val.append(v)
-        cols.append(cols[-1] + len(nz))
-    sub_gene = np.full((L, nL + nR), -1, dtype=np.int32)
-    for l in range(L):
-        k_l, k_r = rng.integers(1, nL + 1), rng.integers(1, nR + 1)
-        genes = rng.choice(G, size=k_l + k_r, replace=(G < k_l + k_r))
-        sub_gene[l, :k_l] = genes[:k_l]
-        sub_gene[l, nL:nL + k_r] = genes[k_l:]
-    row_lri = rng.integers(0, L, size=R).astype(np.int32)
-    row_emit = rng.integers(0, T, size=R).astype(np.int32)
-    row_recv = rng.integers(0, T, size=R).astype(np.int32)
-    ncols = 1 if C == 1 else 3 + nL + nR
-    prob = PermutationProblem(
-        n_cells=N, n_genes=G, n_celltypes=T, n_conditions=C, max_nL=nL, max_nR=nR,
-        colptr=np.array(cols, dtype=np.int32), rowidx=np.concatenate(idx).astype(np.int32) if cols[-1] else np.zeros(0, np.int32),
-        values=np.concatenate(val) if cols[-1] else np.zeros(0), ct_code=ct, cond_code=cond if C == 2 else None,
-        sub_gene=sub_gene, row_lri=row_lri, row_emit=row_emit, row_recv=row_recv, observed=np.zeros((R, ncols)))
-    return prob, rng
-
-
-def with_tying_observed(prob, rng, n):
-    """Observed = the values of replicate 0 (exact ties), some zeros / sign flips; NaN for absent subunits."""
-    pcond, pct = helpers.reference_like_labels(prob, n, int(rng.integers(1 << 30)))
-    R, C = prob.n_rows, prob.n_conditions
-    if R:
-        _, dist = oracle_c.perm_counts(prob, pct, pcond, return_distributions=True)
-        obs = np.zeros((R, prob.ncols))
-        obs[:, :dist.shape[1]] = dist[0].T
-        if C == 2:
-            obs[:, 3:] = rng.normal(0, 0.5, size=(R, prob.ncols - 3))
-            obs[rng.random(R) < 0.2, 0] *= -1.0                      # |perm| >= |obs| is sign-blind
-            absent = np.asarray(prob.sub_gene)[np.asarray(prob.row_lri)] < 0
-            obs[:, 3:][absent] = np.nan
-        obs[rng.random(R) < 0.1, :1] = 0.0                            # observed 0: every replicate counts
-        prob.observed = obs
-    return pcond, pct
+random_problem = helpers.random_problem
+with_tying_observed = helpers.with_tying_observed
 
 
 CASES = [

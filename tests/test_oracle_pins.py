@@ -159,3 +159,71 @@ def test_oracle_philox_labels_are_stratified_shuffles(liver_cases):
         # counter-based: replicate q does not depend on where the range starts
         cond2, ct2 = oracle_c.philox_labels(prob, 5, seed=3, perm_offset=7)
         assert np.array_equal(ct2, ct[7:12])
+
+
+def _naive_counts(prob, pcond, pct, score_type):
+    """Third, deliberately naive restatement for tiny problems (pure Python loops, dense means): follows
+    run_stat_iteration -> aggregate_cells -> build_cci_or_drate -> counting literally, one replicate at a time."""
+    import math
+    N, G, T, C = prob.n_cells, prob.n_genes, prob.n_celltypes, prob.n_conditions
+    nL, nR = prob.max_nL, prob.max_nR
+    colptr, rowidx, values = np.asarray(prob.colptr), np.asarray(prob.rowidx), np.asarray(prob.values)
+    obs = np.asarray(prob.observed).reshape(prob.n_rows, prob.ncols)
+    sub = np.asarray(prob.sub_gene).reshape(-1, nL + nR)
+    counts = np.zeros(obs.shape, dtype=np.int64)
+
+    def means(group):
+        K = C * T
+        m = [[0.0] * G for _ in range(K)]
+        n = [0] * K
+        for i in range(N):
+            n[group[i]] += 1
+        for g in range(G):
+            for e in range(colptr[g], colptr[g + 1]):
+                m[group[rowidx[e]]][g] += float(values[e])      # ascending cell order inside the column
+        return [[m[k][g] / n[k] for g in range(G)] for k in range(K)]
+
+    def score(m, c, row):
+        l, em, rc = prob.row_lri[row], prob.row_emit[row], prob.row_recv[row]
+        ex = [float("nan") if sub[l, s] < 0 else m[c * T + (em if s < nL else rc)][sub[l, s]] for s in range(nL + nR)]
+        mL = min(v for v in ex[:nL] if not math.isnan(v))
+        mR = min(v for v in ex[nL:] if not math.isnan(v))
+        return (math.sqrt(mL * mR) if score_type == 0 else (mL + mR) / 2), ex
+
+    for q in range(pct.shape[0]):
+        if C == 1:
+            m2 = means([int(x) for x in pct[q]])
+            for r in range(prob.n_rows):
+                counts[r, 0] += score(m2, 0, r)[0] >= obs[r, 0]
+        else:
+            m1 = means([int(pcond[q, i]) * T + int(prob.ct_code[i]) for i in range(N)])
+            m2 = means([int(pcond[q, i]) * T + int(pct[q, i]) for i in range(N)])
+            for r in range(prob.n_rows):
+                (a1, e1), (a2, e2) = score(m1, 0, r), score(m1, 1, r)
+                counts[r, 0] += abs(a2 - a1) >= abs(obs[r, 0])
+                counts[r, 1] += score(m2, 0, r)[0] >= obs[r, 1]
+                counts[r, 2] += score(m2, 1, r)[0] >= obs[r, 2]
+                for s in range(nL + nR):
+                    d = e2[s] - e1[s]
+                    counts[r, 3 + s] += (not math.isnan(d)) and (not math.isnan(obs[r, 3 + s])) and abs(d) >= abs(obs[r, 3 + s])
+    out = counts.astype(float)
+    out[np.isnan(obs)] = np.nan
+    return out
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=21, C=1, N=40, G=4, T=3, L=3, nL=1, nR=2, R=12),
+    dict(seed=22, C=2, N=60, G=5, T=2, L=4, nL=2, nR=3, R=25),
+    dict(seed=23, C=2, N=90, G=6, T=4, L=5, nL=2, nR=2, R=40),
+])
+@pytest.mark.parametrize("score_type", [0, 1])
+def test_c_oracle_equals_naive_python_restatement(kw, score_type):
+    """Tiny random problems with empty gene columns, absent subunits, exact ties between a replicate and the observed
+    values (the `>=` of reference R/utils_permutation.R:141-143 counts them), zero and sign-flipped observed values."""
+    prob, rng = helpers.random_problem(**kw)
+    pcond, pct = helpers.with_tying_observed(prob, rng, 12)
+    want = _naive_counts(prob, pcond, pct, score_type)
+    got, _ = oracle_c.perm_counts(prob, pct, pcond, score_type=score_type)
+    assert np.array_equal(got, want, equal_nan=True)
+    if score_type == 0:
+        assert (got[:, 0] >= 1).all()      # replicate 0 ties with the observed value and is counted
