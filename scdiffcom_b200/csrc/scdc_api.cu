@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -212,7 +213,7 @@ struct scdc_handle {
   DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
   DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
-  DBuf<int> flag;
+  DBuf<int> flag, early_genes;
   double ms_upload = 0;
   size_t mem_total = 0;
   // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
@@ -226,6 +227,11 @@ struct scdc_handle {
     int64_t perm_offset = 0, SB = 0;
     int J = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // detection mode: the group sums of batch 0 were also launched ahead, gene chunk by gene chunk, behind the chunked
+    // upload of the matrix (k2 events bracket them on the handle's stream)
+    bool k2_done = false;
+    int B = 0, k2_launches = 0;
+    cudaEvent_t k2_t0 = nullptr, k2_t1 = nullptr;
   } pre;
 };
 
@@ -233,6 +239,8 @@ namespace {
 
 constexpr int kScoreThreads = 256, kScoreRPT = 2;
 int prelaunch_labels(scdc_handle* h, const scdc_options* o);
+int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, const scdc_options* o,
+                                       std::atomic<int>& genes_valid, std::atomic<bool>& matrix_done, const int& matrix_rc);
 
 int count_sm100_devices(std::vector<int>* ids) {
   int n = 0;
@@ -251,10 +259,12 @@ int count_sm100_devices(std::vector<int>* ids) {
   return found;
 }
 
-// O(nnz) part of the validation: cell indices in range and strictly ascending inside every gene column
-int validate_matrix(const scdc_problem* p) {
+// O(nnz) part of the validation: cell indices in range and strictly ascending inside every gene column.
+// progress (optional) = number of leading gene columns already found valid.
+int validate_matrix(const scdc_problem* p, std::atomic<int>* progress = nullptr) {
   const int N = p->n_cells, G = p->n_genes;
   for (int g = 0; g < G; ++g) {
+    if (progress && (g & 15) == 0) progress->store(g, std::memory_order_release);
     for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) {
       int c = p->rowidx[e];
       if (c < 0 || c >= N) return fail(SCDC_EINVAL, "rowidx out of range at entry %d", e);
@@ -262,6 +272,7 @@ int validate_matrix(const scdc_problem* p) {
         return fail(SCDC_EINVAL, "rowidx not strictly ascending inside gene column %d", g);
     }
   }
+  if (progress) progress->store(G, std::memory_order_release);
   return SCDC_OK;
 }
 
@@ -347,7 +358,7 @@ void scdc_release(scdc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStream_t s0 = h->stream, s1 = h->stream_labels, s2 = h->stream_score;
-  cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1;
+  cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1, e2 = h->pre.k2_t0, e3 = h->pre.k2_t1;
   if (s1) cudaStreamSynchronize(s1);  // e.g. labels drawn ahead of a run that never happened
   if (s2) cudaStreamSynchronize(s2);
   {
@@ -360,6 +371,8 @@ void scdc_release(scdc_handle* h) {
   if (s2) cudaStreamDestroy(s2);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
+  if (e2) cudaEventDestroy(e2);
+  if (e3) cudaEventDestroy(e3);
 }
 
 // Installs the tested rows (sub_cci_template_iter + observed vectors) on a handle: row tables, NA mask, K3 work list,
@@ -469,7 +482,14 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     std::thread& t;
     ~Joiner() { if (t.joinable()) t.join(); }
   } joiner{matrix_check};
-  if (o_hint) matrix_check = std::thread([&]() { matrix_rc = validate_matrix(p); if (matrix_rc) matrix_err = g_err; });
+  std::atomic<int> genes_valid{0};
+  std::atomic<bool> matrix_done{false};
+  if (o_hint)
+    matrix_check = std::thread([&]() {
+      matrix_rc = validate_matrix(p, &genes_valid);
+      if (matrix_rc) matrix_err = g_err;
+      matrix_done.store(true, std::memory_order_release);
+    });
   std::vector<int> ids;
   if (count_sm100_devices(&ids) == 0)
     return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
@@ -543,8 +563,29 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       rc = prelaunch_labels(h.get(), o_hint);
       if (rc) return rc;
     }
-    CU(upload_big(h->rowidx, p->rowidx, h->nnz, s));
-    CU(upload_big(h->values, p->values, h->nnz, s));
+    CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
+    h->sub_gene_h.assign(p->sub_gene, p->sub_gene + (size_t)h->L * h->nS);
+    h->gene_nnz_h.resize(G);
+    for (int g = 0; g < G; ++g) h->gene_nnz_h[g] = p->colptr[g + 1] - p->colptr[g];
+    bool rows_installed = false;
+    if (o_hint && C == 1 && h->pre.valid && !o_hint->return_distributions && !env_int("SCDC_NO_EARLY_REDUCE", 0) &&
+        p->n_rows > 0) {
+      // detection mode, one-shot call: the rows go first (they define the active genes), then the matrix is copied gene
+      // chunk by gene chunk and the group sums of batch 0 are launched behind every chunk, so the copy hides behind compute
+      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
+      if (rc) return rc;
+      rows_installed = true;
+      rc = upload_matrix_with_early_reduction(h.get(), p, o_hint, genes_valid, matrix_done, matrix_rc);
+      if (rc) {
+        if (matrix_check.joinable()) matrix_check.join();
+        cudaDeviceSynchronize();
+        if (matrix_rc) { g_err = matrix_err; return matrix_rc; }
+        return rc;
+      }
+    } else {
+      CU(upload_big(h->rowidx, p->rowidx, h->nnz, s));
+      CU(upload_big(h->values, p->values, h->nnz, s));
+    }
     if (matrix_check.joinable()) {
       matrix_check.join();
       if (matrix_rc) {
@@ -553,10 +594,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
         return matrix_rc;
       }
     }
-    CU(h->sub_gene.upload(p->sub_gene, (size_t)h->L * h->nS, s));
-    h->sub_gene_h.assign(p->sub_gene, p->sub_gene + (size_t)h->L * h->nS);
-    h->gene_nnz_h.resize(G);
-    for (int g = 0; g < G; ++g) h->gene_nnz_h[g] = p->colptr[g + 1] - p->colptr[g];
     pt.lap("create: enqueue uploads");
     std::vector<int> segptr;
     std::unique_ptr<int[]> rows_s;        // not value-initialised: the worker threads first-touch their own ranges
@@ -600,8 +637,10 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       CU(upload_big(h->values_s, vals_s.get(), h->nnz, s));
     }
     pt.lap("create: pass-1 matrix copy");
-    rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
-    if (rc) return rc;
+    if (!rows_installed) {
+      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
+      if (rc) return rc;
+    }
     CU(h->flag.alloc(1));
     pt.lap("create: enqueue rest");
     CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
@@ -677,28 +716,30 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
 
 template <int J, int U, bool PAIR>
 cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                             double* M2, cudaStream_t s) {
+                             double* M2, cudaStream_t s, const int* genes, int n_genes) {
   auto kern = scdc::k_scatter<J, U, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
-  dim3 grid(h->n_active, (nCJ + pl.W - 1) / pl.W);  // active genes only (gene_order)
+  dim3 grid(n_genes, (nCJ + pl.W - 1) / pl.W);  // active genes only (gene_order, or one upload chunk of it)
   kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
-                                        h->ngroup.p, h->gene_order.p, M2);
+                                        h->ngroup.p, genes, M2);
   return cudaGetLastError();
 }
 
 template <int J>
 cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                           double* M2, cudaStream_t s) {
+                           double* M2, cudaStream_t s, const int* genes = nullptr, int n_genes = -1) {
+  if (!genes) { genes = h->gene_order.p; n_genes = h->n_active; }
+  if (n_genes <= 0) return cudaSuccess;
   // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
   const int warps_per_sm = pl.blocks_per_sm * pl.W;
   const int U = env_int("SCDC_U", (J == 1 && warps_per_sm <= 8) ? 16 : 8);
   const int pair = env_int("SCDC_PAIR", (J == 1 && warps_per_sm <= 8) ? 1 : 0);
-  if (J == 1 && U == 16 && pair) return launch_scatter_u<J, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s);
-  if (J == 1 && U == 16) return launch_scatter_u<J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s);
-  if (J == 1 && pair) return launch_scatter_u<J, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s);
-  return launch_scatter_u<J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s);
+  if (J == 1 && U == 16 && pair) return launch_scatter_u<J, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  if (J == 1 && U == 16) return launch_scatter_u<J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  if (J == 1 && pair) return launch_scatter_u<J, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  return launch_scatter_u<J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
 }
 
 int pick_batch(const scdc_handle* h, const scdc_options* o) {
@@ -755,6 +796,84 @@ int prelaunch_labels(scdc_handle* h, const scdc_options* o) {
   return SCDC_OK;
 }
 
+// One-shot call, detection mode: copy the matrix gene chunk by gene chunk and launch the group sums of batch 0 for the
+// active genes of every chunk right behind its copy (same stream), so the pageable H2D copy hides behind compute. A chunk's
+// kernel is launched only once the helper thread has validated that chunk's indices. run_device then skips the group-sum
+// launch of batch 0 (h->pre.k2_done).
+int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, const scdc_options* o,
+                                       std::atomic<int>& genes_valid, std::atomic<bool>& matrix_done, const int& matrix_rc) {
+  cudaStream_t s = h->stream;
+  const int G = h->G, K = h->K;
+  const int B = pick_batch(h, o);
+  const ScatterPlan pl = plan_scatter(h, B);
+  if (pl.J != h->pre.J) {  // cannot happen (same planning inputs); fall back to the plain copy
+    CU(upload_big(h->rowidx, p->rowidx, h->nnz, s));
+    CU(upload_big(h->values, p->values, h->nnz, s));
+    return SCDC_OK;
+  }
+  CU(h->rowidx.alloc(h->nnz));
+  CU(h->values.alloc(h->nnz));
+  CU(h->M2[0].ensure((size_t)(B / 32) * G * K * 32));
+  // chunks: contiguous gene ranges of about equal nnz
+  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(8, h->nnz / (size_t)std::max(1, env_int("SCDC_CHUNK_NNZ", 1 << 20))));
+  std::vector<int> bounds(1, 0);
+  for (int c = 1; c <= n_chunks; ++c) {
+    const long long target = (long long)h->nnz * c / n_chunks;
+    int g = bounds.back();
+    while (g < G && (c == n_chunks || p->colptr[g + 1] <= target)) ++g;
+    bounds.push_back(g);
+  }
+  // active genes of every chunk, in the handle's heavy-first order
+  std::vector<int> order((size_t)h->n_active), by_chunk, off(1, 0);
+  CU(cudaMemcpyAsync(order.data(), h->gene_order.p, order.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int c = 0; c < n_chunks; ++c) {
+    for (int g : order)
+      if (g >= bounds[c] && g < bounds[c + 1]) by_chunk.push_back(g);
+    off.push_back((int)by_chunk.size());
+  }
+  DBuf<int>& d_list = h->early_genes;
+  CU(d_list.upload(by_chunk.data(), by_chunk.size(), s));
+  if (!h->pre.k2_t0) { CU(cudaEventCreate(&h->pre.k2_t0)); CU(cudaEventCreate(&h->pre.k2_t1)); }
+  CU(cudaStreamWaitEvent(s, h->pre.t1, 0));  // labels of super-batch 0
+  // The copies go on their own stream: a pageable cudaMemcpyAsync waits for the work queued before it on ITS stream, so on
+  // the compute stream every chunk's copy would wait for the previous chunk's kernel.
+  cudaStream_t sc = h->stream_score;
+  cudaEvent_t copied;
+  CU(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+  struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } evdel{copied};
+  {  // the copy stream must see the allocations made on the compute stream
+    CU(cudaEventRecord(copied, s));
+    CU(cudaStreamWaitEvent(sc, copied, 0));
+  }
+  bool first = true;
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t e0 = (size_t)p->colptr[bounds[c]], e1 = (size_t)p->colptr[bounds[c + 1]];
+    if (e1 > e0) {
+      CU(cudaMemcpyAsync(h->rowidx.p + e0, p->rowidx + e0, (e1 - e0) * sizeof(int), cudaMemcpyHostToDevice, sc));
+      CU(cudaMemcpyAsync(h->values.p + e0, p->values + e0, (e1 - e0) * sizeof(double), cudaMemcpyHostToDevice, sc));
+    }
+    CU(cudaEventRecord(copied, sc));
+    CU(cudaStreamWaitEvent(s, copied, 0));
+    while (genes_valid.load(std::memory_order_acquire) < bounds[c + 1] && !matrix_done.load(std::memory_order_acquire))
+      std::this_thread::yield();
+    if (matrix_done.load(std::memory_order_acquire) && matrix_rc != SCDC_OK)
+      return fail(SCDC_EINVAL, "matrix validation failed");  // the caller reports the helper thread's message
+    if (first) { CU(cudaEventRecord(h->pre.k2_t0, s)); first = false; }
+    const int n_g = off[c + 1] - off[c];
+    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g)
+                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g)
+                                   : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g);
+    CU(le);
+  }
+  if (first) CU(cudaEventRecord(h->pre.k2_t0, s));
+  CU(cudaEventRecord(h->pre.k2_t1, s));
+  h->pre.k2_done = true;
+  h->pre.B = B;
+  h->pre.k2_launches = n_chunks;
+  return SCDC_OK;
+}
+
 // Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
 // h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
 int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st, cudaStream_t s) {
@@ -773,7 +892,9 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   const int64_t SB = uploaded ? B : pick_super_batch(h, o, B);
   const bool pre_ok = !uploaded && h->pre.valid && h->pre.seed == o->seed && h->pre.perm_offset == o->perm_offset &&
                       h->pre.SB == SB && h->pre.J == pl.J;
+  const bool early_k2 = pre_ok && h->pre.k2_done && h->pre.B == B && C == 1 && s == h->stream;
   h->pre.valid = false;  // consumed (or stale)
+  h->pre.k2_done = false;
   const int SBw = (int)(SB / 32);
   const bool pipelined = !uploaded && SB < iters_pad;
   const int nbuf = pipelined ? 2 : 1;
@@ -922,11 +1043,16 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(cudaGetLastError());
       ++launches; ++reduce_launches;
     }
-    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, B, M2b, s)
-                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, B, M2b, s)
-                                   : launch_scatter<1>(h, pl, B, lab2_b, B, M2b, s);
-    CU(le);
-    ++launches; ++reduce_launches;
+    if (early_k2 && done == 0) {
+      launches += h->pre.k2_launches;  // batch 0 was reduced behind the matrix upload (upload_matrix_with_early_reduction)
+      reduce_launches += h->pre.k2_launches;
+    } else {
+      cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, B, M2b, s)
+                       : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, B, M2b, s)
+                                     : launch_scatter<1>(h, pl, B, lab2_b, B, M2b, s);
+      CU(le);
+      ++launches; ++reduce_launches;
+    }
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
@@ -1030,6 +1156,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       float a = 0;
       cudaEventElapsedTime(&a, h->pre.t0, h->pre.t1);
       st->ms_labels += a;  // drawn during scdc_create, overlapped with the matrix upload
+    }
+    if (early_k2) {
+      float a = 0;
+      cudaEventElapsedTime(&a, h->pre.k2_t0, h->pre.k2_t1);
+      st->ms_reduce += a;  // includes the interleaved H2D chunks it hides
     }
     for (size_t i = 0; i + 1 < evl.size(); i += 2) {
       float a = 0;
