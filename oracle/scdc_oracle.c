@@ -201,6 +201,43 @@ static int urn_pick(uint32_t* n, int T, uint32_t u) {
   return -1;
 }
 
+/* Detection mode, random-key generator (mirrors keygen_plan / k_draw_labels_keys of scdc_kernels.cuh): cell i has the key
+ * (A_i, B_i, i), A_i = element i % 4 of Philox block (i / 4, 0x80000000, replicate), B_i the same with c1 = 0x80000001;
+ * the cells sorted by key receive the labels 0 x n_0, 1 x n_1, ... in that order. */
+static int keygen_applies(int N, int T, int C) {
+  if (C != 1 || T < 2) return 0;
+  int NB = 256;
+  while (NB < 32768 && (long long)NB * 8 < N) NB <<= 1;
+  const double mean = (double)N / NB;
+  if (mean > 32.0) return 0;
+  const int cap = (mean <= 8.0) ? 64 : 128;
+  const long long smem = 4LL * (NB + 1) + 4LL * NB / 32 + (long long)(T - 1) * cap * 8 + 4LL * 8 * T + 256;
+  return smem <= 180 * 1024;
+}
+typedef struct { uint32_t a, b, i; } keyrec;
+static int keyrec_cmp(const void* x, const void* y) {
+  const keyrec *p = (const keyrec*)x, *q = (const keyrec*)y;
+  if (p->a != q->a) return p->a < q->a ? -1 : 1;
+  if (p->b != q->b) return p->b < q->b ? -1 : 1;
+  return p->i < q->i ? -1 : (p->i > q->i);
+}
+static int keygen_labels(int N, int T, const uint32_t* counts, uint64_t seed, uint64_t rep, uint8_t* ct_out) {
+  keyrec* rec = (keyrec*)malloc(sizeof(keyrec) * (size_t)N);
+  if (!rec) return 1;
+  for (int i = 0; i < N; ++i) {
+    uint32_t wa[4], wb[4];
+    philox4x32_10((uint32_t)i >> 2, 0x80000000u, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), wa);
+    philox4x32_10((uint32_t)i >> 2, 0x80000001u, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), wb);
+    rec[i].a = wa[i & 3]; rec[i].b = wb[i & 3]; rec[i].i = (uint32_t)i;
+  }
+  qsort(rec, (size_t)N, sizeof(keyrec), keyrec_cmp);
+  int pos = 0;
+  for (int k = 0; k < T; ++k)
+    for (uint32_t c = 0; c < counts[k]; ++c) ct_out[rec[pos++].i] = (uint8_t)k;
+  free(rec);
+  return 0;
+}
+
 int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int32_t* cond_code, uint64_t seed,
                          int64_t perm_offset, int64_t n, uint8_t* cond_out, uint8_t* ct_out) {
   uint32_t* base = (uint32_t*)calloc((size_t)2 * T, sizeof(uint32_t));
@@ -209,6 +246,13 @@ int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int3
   int32_t* visit = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
   if (!base || !remc || !urn || !visit) return 1;
   for (int i = 0; i < N; ++i) ++base[(size_t)((C == 2) ? cond_code[i] : 0) * T + ct_code[i]];
+  if (keygen_applies(N, T, C)) {
+    int rc = 0;
+    for (int64_t q = 0; q < n && !rc; ++q)
+      rc = keygen_labels(N, T, base, seed, (uint64_t)(perm_offset + q), ct_out + (size_t)q * N);
+    free(base); free(remc); free(urn); free(visit);
+    return rc;
+  }
   if (C == 2) { /* stable sort of the cells by cell type */
     int v = 0;
     for (int t = 0; t < T; ++t)

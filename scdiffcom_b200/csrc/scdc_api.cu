@@ -213,7 +213,8 @@ struct scdc_handle {
   DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
   DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
-  DBuf<int> flag, early_genes;
+  DBuf<int> flag, early_genes, keyfail;   // keyfail: overflow flag of the random-key label generator
+  DBuf<uint8_t> label_tmp;               // replicate-major labels of the random-key generator before re-layout
   double ms_upload = 0;
   size_t mem_total = 0;
   // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
@@ -673,10 +674,48 @@ cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, 
   return cudaGetLastError();
 }
 
-// B = replicates drawn by this launch (a multiple of Bb), Bb = replicates per reduction batch (label block size)
-cudaError_t launch_draw(const scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
+// B = replicates drawn by this launch (a multiple of Bb), Bb = replicates per reduction batch (label block size).
+// Detection mode uses the parallel random-key generator (one block per replicate) when keygen_plan allows it, else the
+// sequential urn generator (one thread per replicate); oracle_philox_labels mirrors the same rule.
+cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
                         uint32_t* bits1, uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
   const int T = h->T;
+  const scdc::KeygenPlan kp = scdc::keygen_plan(h->N, T, h->C);
+  if (kp.ok && !env_int("SCDC_URN_LABELS", 0)) {
+    auto kern = scdc::k_draw_labels_keys;
+    cudaError_t e = cudaSuccess;
+    if (kp.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem);
+    if (e != cudaSuccess) return e;
+    if (!h->keyfail.p) {
+      e = h->keyfail.alloc(1);
+      if (e == cudaSuccess) e = cudaMemsetAsync(h->keyfail.p, 0, sizeof(int), g_alloc_async ? g_alloc_stream : s);
+      if (e != cudaSuccess) return e;
+    }
+    uint8_t* out = dbg_ct;
+    if (!out) {
+      e = h->label_tmp.ensure((size_t)h->N * B);
+      if (e != cudaSuccess) return e;
+      out = h->label_tmp.p;
+    }
+    if (s != g_alloc_stream && g_alloc_async) {  // buffers are allocated in the order of the allocation stream
+      cudaEvent_t dep;
+      e = cudaEventCreateWithFlags(&dep, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      cudaError_t e1 = cudaEventRecord(dep, g_alloc_stream), e2 = cudaStreamWaitEvent(s, dep, 0);
+      cudaEventDestroy(dep);
+      if (e1 != cudaSuccess) return e1;
+      if (e2 != cudaSuccess) return e2;
+    }
+    kern<<<B, 256, kp.smem, s>>>(h->N, T, h->expect.p, seed, perm0, kp.NB, kp.cap, out, h->keyfail.p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || dbg_ct) return e;
+    for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks of the reduction
+      dim3 grid((h->N + 31) / 32, Bb / 32), block(32, 32);
+      scdc::k_pack_uploaded<<<grid, block, 0, s>>>(h->N, T, 1, Bb, Bb, J, h->ct.p, h->cond.p, nullptr,
+                                                   out + (size_t)b0 * h->N, nullptr, lab2 + (size_t)b0 * h->N);
+    }
+    return cudaGetLastError();
+  }
   if (T <= 16) return launch_draw_ng<2>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
   if (T <= 32) return launch_draw_ng<4>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
   if (T <= 64) return launch_draw_ng<8>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
@@ -1130,6 +1169,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   }
   CU(cudaStreamSynchronize(s));
   if (pipelined) CU(cudaStreamSynchronize(sL));
+  if (h->keyfail.p) {
+    int kf = 0;
+    CU(cudaMemcpy(&kf, h->keyfail.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (kf) return fail(SCDC_ECUDA, "internal: the random-key label generator overflowed a target bin (probability < 1e-30)");
+  }
   if (uploaded) {
     int flag = 0;
     CU(cudaMemcpy(&flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost));

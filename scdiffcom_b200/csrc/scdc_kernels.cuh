@@ -194,6 +194,217 @@ __global__ void __launch_bounds__(32) k_draw_labels(int N, int T, int C, const i
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K1k: detection-mode label shuffles by RANDOM KEYS, one thread block per replicate (fully parallel over the cells).
+// Cell i gets the key (A_i, B_i, i): A_i = element i % 4 of Philox block (i / 4, 0x80000000, replicate), B_i likewise with
+// c1 = 0x80000001 (only evaluated to break a tie on A). Sorting the cells by key is a uniformly random permutation; the
+// first n_0 cells of that order receive label 0, the next n_1 label 1, ... (the distribution of sample(cell_type),
+// reference R/utils_permutation.R:509). No sort is needed: label(i) = #{j : theta_j <= key_i} where theta_j is the cell
+// of rank C_j = n_0 + .. + n_j, found by histogram selection:
+//   pass 1  histogram of the top bits of A (NB bins, shared-memory atomics), exclusive scan;
+//   targets each rank C_j falls into one bin; the members of the target bins are collected (pass 2, <= cap per target) and
+//           the member with the right rank inside the bin is the threshold theta_j;
+//   pass 3  every cell compares its key with the T-1 thresholds (binary search) and writes its label.
+// Output: replicate-major labels out[q][cell] (re-laid out by k_pack_uploaded). fail[0] is set if a target bin holds more
+// than cap cells (probability < 1e-30 with the NB / cap chosen by keygen_plan).
+// ------------------------------------------------------------------------------------------------------------------
+struct KeygenPlan {
+  int ok;     // 1: the random-key generator applies, 0: use the sequential urn generator
+  int NB;     // histogram bins (power of two)
+  int cap;    // members kept per target bin
+  int smem;   // dynamic shared memory in bytes
+};
+
+__host__ __device__ inline KeygenPlan keygen_plan(int N, int T, int C) {
+  KeygenPlan pl = {0, 0, 0, 0};
+  if (C != 1 || T < 2) return pl;
+  int NB = 256;
+  while (NB < 32768 && (long long)NB * 8 < N) NB <<= 1;
+  const double mean = (double)N / NB;
+  if (mean > 32.0) return pl;
+  const int cap = (mean <= 8.0) ? 64 : 128;
+  const long long smem = 4LL * (NB + 1) + 4LL * NB / 32 + (long long)(T - 1) * cap * 8 + 4LL * 8 * T + 256;
+  if (smem > 180 * 1024) return pl;
+  pl.ok = 1; pl.NB = NB; pl.cap = cap; pl.smem = (int)smem;
+  return pl;
+}
+
+__device__ __forceinline__ uint32_t keygen_word(uint32_t i, uint32_t stream, uint32_t r_lo, uint32_t r_hi, uint32_t k0, uint32_t k1) {
+  uint32_t w[4];
+  philox4x32_10(i >> 2, 0x80000000u | stream, r_lo, r_hi, k0, k1, w);
+  return w[i & 3];
+}
+
+// (a_x, b_x, x) < (a_y, b_y, y) with the B words evaluated only on a tie of the A words
+__device__ __forceinline__ bool keygen_less(uint32_t ax, uint32_t x, uint32_t ay, uint32_t y, uint32_t r_lo, uint32_t r_hi,
+                                            uint32_t k0, uint32_t k1) {
+  if (ax != ay) return ax < ay;
+  const uint32_t bx = keygen_word(x, 1u, r_lo, r_hi, k0, k1), by = keygen_word(y, 1u, r_lo, r_hi, k0, k1);
+  if (bx != by) return bx < by;
+  return x < y;
+}
+
+__global__ void __launch_bounds__(256) k_draw_labels_keys(int N, int T, const uint32_t* __restrict__ ngroup_u, uint64_t seed,
+                                                          int64_t perm0, int NB, int cap, uint8_t* __restrict__ out,
+                                                          int* __restrict__ fail) {
+  extern __shared__ uint32_t sm_k[];
+  const int tid = threadIdx.x, nthr = blockDim.x, m = T - 1;
+  const int q = blockIdx.x;
+  const uint64_t rep = (uint64_t)(perm0 + q);
+  const uint32_t r_lo = (uint32_t)rep, r_hi = (uint32_t)(rep >> 32), k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  int lg = 0;
+  while ((1 << lg) < NB) ++lg;
+  const int shift = 32 - lg;
+  uint32_t* hist = sm_k;                       // [NB + 1] counts, then exclusive prefix
+  uint32_t* mark = hist + NB + 1;              // [NB / 32] bitmap of target bins
+  uint32_t* tbin = mark + NB / 32;             // [m] bin of target j (ascending in j)
+  uint32_t* tq = tbin + m;                     // [m] rank of the threshold inside its bin
+  uint32_t* lcnt = tq + m;                     // [m] members collected
+  uint32_t* thrA = lcnt + m;                   // [m] thresholds: A word, B word, cell
+  uint32_t* thrB = thrA + m;
+  uint32_t* thrI = thrB + m;
+  uint32_t* wsum = thrI + m;                   // [32] scan scratch
+  uint32_t* lkey = wsum + 32;                  // [m][cap]
+  uint32_t* lidx = lkey + m * cap;             // [m][cap]
+  for (int b = tid; b <= NB; b += nthr) hist[b] = 0;
+  for (int b = tid; b < NB / 32; b += nthr) mark[b] = 0;
+  for (int j = tid; j < m; j += nthr) lcnt[j] = 0;
+  __syncthreads();
+  // ---- pass 1: histogram of the top bits of A ----
+  for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i4 + k < N) atomicAdd(&hist[w[k] >> shift], 1u);
+  }
+  __syncthreads();
+  // ---- exclusive scan of the NB bins (NB / nthr consecutive bins per thread) ----
+  {
+    const int per = NB / nthr;  // NB >= 256 = nthr
+    uint32_t loc = 0;
+    for (int k = 0; k < per; ++k) loc += hist[tid * per + k];
+    uint32_t inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+      if ((tid & 31) >= d) inc += v;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t v = (tid < nthr / 32) ? wsum[tid] : 0, iv = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, iv, d);
+        if (tid >= d) iv += u;
+      }
+      wsum[tid] = iv - v;  // exclusive warp offsets
+    }
+    __syncthreads();
+    uint32_t run = wsum[tid >> 5] + inc - loc;
+    for (int k = 0; k < per; ++k) {
+      const uint32_t c = hist[tid * per + k];
+      hist[tid * per + k] = run;
+      run += c;
+    }
+    if (tid == nthr - 1) hist[NB] = run;
+  }
+  __syncthreads();
+  // ---- targets: rank C_j -> (bin, rank inside the bin) ----
+  for (int j = tid; j < m; j += nthr) {
+    uint32_t r = 0;
+    for (int k = 0; k <= j; ++k) r += ngroup_u[k];
+    int lo = 0, hi = NB;  // first bin with prefix > r
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (hist[mid + 1] > r) hi = mid; else lo = mid + 1;
+    }
+    tbin[j] = (uint32_t)lo;
+    tq[j] = r - hist[lo];
+    atomicOr(&mark[lo >> 5], 1u << (lo & 31));
+  }
+  __syncthreads();
+  // ---- pass 2: collect the members of the target bins ----
+  for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i4 + k >= N) continue;
+      const uint32_t bin = w[k] >> shift;
+      if (!((mark[bin >> 5] >> (bin & 31)) & 1u)) continue;
+      int lo = 0, hi = m;  // first target with tbin >= bin
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tbin[mid] >= bin) hi = mid; else lo = mid + 1;
+      }
+      for (int j = lo; j < m && tbin[j] == bin; ++j) {
+        const uint32_t pos = atomicAdd(&lcnt[j], 1u);
+        if (pos < (uint32_t)cap) { lkey[j * cap + pos] = w[k]; lidx[j * cap + pos] = (uint32_t)(i4 + k); }
+        else atomicExch(fail, 1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- thresholds: the member with tq[j] smaller members ----
+  for (int pair = tid; pair < m * cap; pair += nthr) {
+    const int j = pair / cap, x = pair % cap;
+    const int mj = min((int)lcnt[j], cap);
+    if (x >= mj) continue;
+    const uint32_t ax = lkey[j * cap + x], ix = lidx[j * cap + x];
+    uint32_t less = 0;
+    for (int y = 0; y < mj; ++y)
+      if (y != x && keygen_less(lkey[j * cap + y], lidx[j * cap + y], ax, ix, r_lo, r_hi, k0, k1)) ++less;
+    if (less == tq[j]) {
+      thrA[j] = ax;
+      thrI[j] = ix;
+      thrB[j] = keygen_word(ix, 1u, r_lo, r_hi, k0, k1);
+    }
+  }
+  __syncthreads();
+  // ---- pass 3: label = number of thresholds <= key ----
+  uint8_t* o = out + (size_t)q * N;
+  const bool aligned = (reinterpret_cast<size_t>(o) & 3) == 0;
+  for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = (uint32_t)(i4 + k), a = w[k];
+      const uint32_t bin = a >> shift;
+      int lo = 0, hi = m;  // first threshold > key
+      if (!((mark[bin >> 5] >> (bin & 31)) & 1u)) {
+        // not a target bin: every threshold lies in another bin, so only the bins need comparing (first tbin > bin)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (tbin[mid] < bin) lo = mid + 1; else hi = mid;
+        }
+        packed |= (uint32_t)lo << (8 * k);
+        continue;
+      }
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        bool thr_le;  // theta_mid <= key_i
+        if (thrA[mid] != a) thr_le = thrA[mid] < a;
+        else if (thrI[mid] == i) thr_le = true;
+        else {
+          const uint32_t b = keygen_word(i, 1u, r_lo, r_hi, k0, k1);
+          thr_le = (thrB[mid] != b) ? (thrB[mid] < b) : (thrI[mid] < i);
+        }
+        if (thr_le) lo = mid + 1; else hi = mid;
+      }
+      packed |= (uint32_t)lo << (8 * k);
+    }
+    if (aligned && i4 + 3 < N) {
+      *reinterpret_cast<uint32_t*>(o + i4) = packed;
+    } else {
+      for (int k = 0; k < 4 && i4 + k < N; ++k) o[i4 + k] = (uint8_t)(packed >> (8 * k));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K1u: validation mode. up_ct / up_cond are replicate-major [nb][N]; writes the same device layouts as K1.
 // Replicates q >= nb (padding) get the original labels (results for them are never counted).
 // grid = (ceil(N/32), Bpad/32), block = (32, 32): threadIdx.x = replicate in word, threadIdx.y = cell in tile.
