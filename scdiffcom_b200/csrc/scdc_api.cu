@@ -710,9 +710,8 @@ cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t p
     e = cudaGetLastError();
     if (e != cudaSuccess || dbg_ct) return e;
     for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks of the reduction
-      dim3 grid((h->N + 31) / 32, Bb / 32), block(32, 32);
-      scdc::k_pack_uploaded<<<grid, block, 0, s>>>(h->N, T, 1, Bb, Bb, J, h->ct.p, h->cond.p, nullptr,
-                                                   out + (size_t)b0 * h->N, nullptr, lab2 + (size_t)b0 * h->N);
+      dim3 grid((h->N + 127) / 128, Bb / 128);
+      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N);
     }
     return cudaGetLastError();
   }

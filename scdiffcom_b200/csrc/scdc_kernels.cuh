@@ -442,6 +442,41 @@ __global__ void k_pack_uploaded(int N, int T, int C, int nb, int Bpad, int J, co
   }
 }
 
+// Re-layout of the random-key generator's replicate-major labels in[rep][cell] (detection mode) into one reduction batch
+// block out[cell][Bb] (J labels of a lane adjacent). Tile = 128 replicates x 128 cells through shared memory: 128-byte
+// coalesced reads of a replicate's cells, 128-byte coalesced writes of a cell's replicates. grid = (ceil(N/128), Bb/128).
+__global__ void __launch_bounds__(256) k_relayout_labels(int N, int Bb, int J, const uint8_t* __restrict__ in,
+                                                         uint8_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t tile[128][132];
+  const int cell0 = blockIdx.x * 128, rep0 = blockIdx.y * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fast = (N & 3) == 0;  // rows of `in` are then 4-byte aligned
+  for (int rr = warp; rr < 128; rr += 8) {
+    const uint8_t* row = in + (size_t)(rep0 + rr) * N + cell0;
+    const int c = lane * 4;
+    if (fast && cell0 + c + 3 < N) {
+      *reinterpret_cast<uint32_t*>(&tile[rr][c]) = *reinterpret_cast<const uint32_t*>(row + c);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tile[rr][c + k] = (cell0 + c + k < N) ? row[c + k] : 0;
+    }
+  }
+  __syncthreads();
+  const int cs = 32 * J;  // replicates per chunk
+  for (int item = threadIdx.x; item < 128 * 32; item += 256) {
+    const int c = item >> 5, wd = item & 31;
+    if (cell0 + c >= N) continue;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = wd * 4 + k, chunk = b / cs, bb = b % cs;
+      const int rep = chunk * cs + (bb % J) * 32 + bb / J;
+      packed |= (uint32_t)tile[rep][c] << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(out + (size_t)(cell0 + c) * Bb + rep0 + wd * 4) = packed;
+  }
+}
+
 // validation of uploaded labels: every replicate must keep n(cell type, condition) of both passes
 // (R/utils_permutation.R:536-569 guarantees it). One block per replicate. flag[0] != 0 on violation or bad code.
 __global__ void k_check_uploaded(int N, int T, int C, const uint8_t* __restrict__ ct, const uint8_t* __restrict__ up_cond,
