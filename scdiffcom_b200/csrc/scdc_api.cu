@@ -379,19 +379,10 @@ void scdc_release(scdc_handle* h) {
 // Installs the tested rows (sub_cci_template_iter + observed vectors) on a handle: row tables, NA mask, K3 work list,
 // product thresholds, factorisation table of the subunit columns, and the list of ACTIVE genes (the genes the rows
 // reference — the reference's gene subset of data_tr, R/utils_permutation.R:79-84 — heaviest column first).
-static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv,
-                        const double* observed) {
+// Part 1 of install_rows: the list of active genes (all the group sums need from the rows).
+static int install_active_genes(scdc_handle* h, int n_rows, const int32_t* row_lri) {
   cudaStream_t s = h->stream;
-  const int T = h->T, C = h->C, G = h->G;
-  h->R = n_rows;
-  PhaseTimer pt;
-  CU(h->row_lri.upload(row_lri, n_rows, s));
-  CU(h->row_emit.upload(row_emit, n_rows, s));
-  CU(h->row_recv.upload(row_recv, n_rows, s));
-  CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
-  h->obs_na.resize((size_t)n_rows * h->ncols);
-  for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
-  // active genes
+  const int G = h->G;
   std::vector<uint8_t> lri_used((size_t)h->L, 0), gene_used((size_t)G, 0);
   for (int r = 0; r < n_rows; ++r) lri_used[row_lri[r]] = 1;
   for (int l = 0; l < h->L; ++l)
@@ -407,6 +398,29 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->gene_nnz_h[a] > h->gene_nnz_h[b]; });
   h->n_active = (int)order.size();
   CU(h->gene_order.upload(order.data(), order.size(), s));
+  CU(cudaStreamSynchronize(s));  // host staging vector dies at scope exit
+  return SCDC_OK;
+}
+
+// `up` != NULL: the active genes are installed already and the group sums of batch 0 are running on the handle's streams;
+// allocate, copy and launch on `up` instead (an idle stream), and make the handle's stream wait for it at the end.
+static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv,
+                        const double* observed, cudaStream_t up = nullptr) {
+  cudaStream_t s = up ? up : h->stream;
+  AllocScope alloc_scope(s);
+  const int T = h->T, C = h->C;
+  h->R = n_rows;
+  PhaseTimer pt;
+  if (!up) {
+    int rc = install_active_genes(h, n_rows, row_lri);
+    if (rc) return rc;
+  }
+  CU(h->row_lri.upload(row_lri, n_rows, s));
+  CU(h->row_emit.upload(row_emit, n_rows, s));
+  CU(h->row_recv.upload(row_recv, n_rows, s));
+  CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
+  h->obs_na.resize((size_t)n_rows * h->ncols);
+  for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
   // K3 work list: rows stably sorted by LRI (counting sort), each LRI cut into slices of score_threads * kScoreRPT rows
   std::vector<int> srow(n_rows), t_lri, t_beg, t_end;
   {
@@ -464,6 +478,14 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   CU(h->task_end.upload(t_end.data(), t_end.size(), s));
   pt.lap("rows: enqueue rest");
   CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+  if (up) {
+    cudaEvent_t done;
+    CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(done, up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, done, 0);
+    cudaEventDestroy(done);
+    CU(e);
+  }
   return SCDC_OK;
 }
 
@@ -573,9 +595,9 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
         p->n_rows > 0) {
       // detection mode, one-shot call: the rows go first (they define the active genes), then the matrix is copied gene
       // chunk by gene chunk and the group sums of batch 0 are launched behind every chunk, so the copy hides behind compute
-      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
+      h->R = p->n_rows;
+      rc = install_active_genes(h.get(), p->n_rows, p->row_lri);
       if (rc) return rc;
-      rows_installed = true;
       rc = upload_matrix_with_early_reduction(h.get(), p, o_hint, genes_valid, matrix_done, matrix_rc);
       if (rc) {
         if (matrix_check.joinable()) matrix_check.join();
@@ -583,6 +605,10 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
         if (matrix_rc) { g_err = matrix_err; return matrix_rc; }
         return rc;
       }
+      // the rest of the rows (K3's inputs) goes up on the copy stream while the group sums run
+      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed, h->stream_score);
+      if (rc) return rc;
+      rows_installed = true;
     } else {
       CU(upload_big(h->rowidx, p->rowidx, h->nnz, s));
       CU(upload_big(h->values, p->values, h->nnz, s));
@@ -853,7 +879,7 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
   CU(h->values.alloc(h->nnz));
   CU(h->M2[0].ensure((size_t)(B / 32) * G * K * 32));
   // chunks: contiguous gene ranges of about equal nnz
-  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(8, h->nnz / (size_t)std::max(1, env_int("SCDC_CHUNK_NNZ", 1 << 20))));
+  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(16, h->nnz / (size_t)std::max(1, env_int("SCDC_CHUNK_NNZ", 1 << 19))));
   std::vector<int> bounds(1, 0);
   for (int c = 1; c <= n_chunks; ++c) {
     const long long target = (long long)h->nnz * c / n_chunks;
@@ -885,26 +911,50 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
     CU(cudaStreamWaitEvent(sc, copied, 0));
   }
   bool first = true;
+  const bool dbg = getenv("SCDC_TIMING") != nullptr;
+  std::vector<cudaEvent_t> dbg_ev;
+  std::vector<double> dbg_host;
+  const double dbg_t0 = now_ms();
+  if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sc); dbg_ev.push_back(e); }
   for (int c = 0; c < n_chunks; ++c) {
     const size_t e0 = (size_t)p->colptr[bounds[c]], e1 = (size_t)p->colptr[bounds[c + 1]];
     if (e1 > e0) {
       CU(cudaMemcpyAsync(h->rowidx.p + e0, p->rowidx + e0, (e1 - e0) * sizeof(int), cudaMemcpyHostToDevice, sc));
       CU(cudaMemcpyAsync(h->values.p + e0, p->values + e0, (e1 - e0) * sizeof(double), cudaMemcpyHostToDevice, sc));
     }
+    // chunk kernels alternate between two streams so that the tail of one chunk overlaps the head of the next
+    cudaStream_t sk = (c & 1) ? h->stream_labels : s;
     CU(cudaEventRecord(copied, sc));
-    CU(cudaStreamWaitEvent(s, copied, 0));
+    CU(cudaStreamWaitEvent(sk, copied, 0));
     while (genes_valid.load(std::memory_order_acquire) < bounds[c + 1] && !matrix_done.load(std::memory_order_acquire))
       std::this_thread::yield();
     if (matrix_done.load(std::memory_order_acquire) && matrix_rc != SCDC_OK)
       return fail(SCDC_EINVAL, "matrix validation failed");  // the caller reports the helper thread's message
-    if (first) { CU(cudaEventRecord(h->pre.k2_t0, s)); first = false; }
+    if (first) {
+      CU(cudaEventRecord(h->pre.k2_t0, s));
+      CU(cudaStreamWaitEvent(h->stream_labels, h->pre.k2_t0, 0));  // allocations, labels, gene list
+      first = false;
+    }
     const int n_g = off[c + 1] - off[c];
-    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g)
-                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g)
-                                   : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s, d_list.p + off[c], n_g);
+    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g)
+                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g)
+                                   : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g);
     CU(le);
+    if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sk); dbg_ev.push_back(e); dbg_host.push_back(now_ms() - dbg_t0); }
+  }
+  if (dbg) {
+    cudaStreamSynchronize(s); cudaStreamSynchronize(h->stream_labels);
+    for (size_t i = 1; i < dbg_ev.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[0], dbg_ev[i]);
+      fprintf(stderr, "[scdc timing]   chunk %zu: launched at host %.2f ms, K2 done at device %.2f ms\n", i - 1, dbg_host[i - 1], ms);
+    }
+    float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[0], h->pre.t1);
+    fprintf(stderr, "[scdc timing]   labels ready at device %.2f ms\n", ms);
+    for (auto e : dbg_ev) cudaEventDestroy(e);
   }
   if (first) CU(cudaEventRecord(h->pre.k2_t0, s));
+  CU(cudaEventRecord(copied, h->stream_labels));  // join the second kernel stream
+  CU(cudaStreamWaitEvent(s, copied, 0));
   CU(cudaEventRecord(h->pre.k2_t1, s));
   h->pre.k2_done = true;
   h->pre.B = B;

@@ -287,7 +287,7 @@ def test_full_size_identity_labels_reproduce_the_observed_pass(name):
 
 def test_one_shot_detection_call_reduces_batch_0_behind_the_chunked_upload(liver_cases, monkeypatch):
     """scdc_perm_counts, detection mode: the matrix is copied gene chunk by gene chunk with the group sums of batch 0
-    launched behind every chunk. Forced to 8 chunks on the small fixture; results must not change."""
+    launched behind every chunk. Forced to many small chunks on the small fixture; results must not change."""
     prob = liver_cases["nocond"]["prob"]
     cond_o, ct_o = oracle_c.philox_labels(prob, 700, seed=31)
     want, _ = oracle_c.perm_counts(prob, ct_o, cond_o)
@@ -297,4 +297,6 @@ def test_one_shot_detection_call_reduces_batch_0_behind_the_chunked_upload(liver
     b = perm_counts(prob, 700, seed=31, batch_size=256)
     assert np.array_equal(a["counts"], want, equal_nan=True)
     assert np.array_equal(b["counts"], want, equal_nan=True)
-    assert a["stats"]["reduce_launches"] == 8 + 2 and b["stats"]["reduce_launches"] == 3
+    n_chunks = min(16, prob.nnz // 5000)
+    assert n_chunks >= 8
+    assert a["stats"]["reduce_launches"] == n_chunks + 2 and b["stats"]["reduce_launches"] == 3
