@@ -98,12 +98,13 @@ def build_workload(name):
     return prob, cfg
 
 
-def workload_config(name, prob, cfg, extra):
+def workload_config(name, prob, cfg, extra, iters=None):
+    iters = int(iters or cfg["iterations"])
     c = {"workload": f"{name}: synthetic {prob.n_cells} cells x {prob.n_genes} LRI genes (of {cfg['n_genes']}), "
                      f"{prob.n_celltypes} cell types, {'differential' if prob.n_conditions == 2 else 'single-condition'} mode, "
-                     f"{cfg['iterations']} permutations per GPU",
+                     f"{iters} permutations per GPU",
          "nnz": prob.nnz, "tested_rows": prob.n_rows, "counters_per_row": prob.ncols, "n_lri": prob.n_lri,
-         "iterations_per_gpu": cfg["iterations"], "seed": cfg["seed"]}
+         "iterations_per_gpu": iters, "seed": cfg["seed"]}
     c.update(extra)
     return c
 
@@ -225,7 +226,7 @@ def run_ours(args):
 
     # ---- e2e: one-shot C-ABI call with host buffers (H2D + D2H inside the timed region) ----
     e2e_steps = max(1, args.steps)
-    for _ in range(max(3, args.warmup)):   # warm-up (the first cudaMalloc / cudaFree cycles of new sizes are slow)
+    for _ in range(args.e2e_warmup or max(3, args.warmup)):   # warm-up (the first cudaMalloc / cudaFree cycles of new sizes are slow)
         perm_counts(prob, iters, seed=seed, perm_offset=rank * iters, device_base=local, batch_size=args.batch)
     barrier()
     e2e_call_ms = []
@@ -235,7 +236,7 @@ def run_ours(args):
         r = perm_counts(prob, iters, seed=seed, perm_offset=rank * iters, device_base=local, batch_size=args.batch)
         e2e_call_ms.append(round((time.perf_counter() - t_call) * 1e3, 2))
         if world > 1:
-            c = torch.from_numpy(np.nan_to_num(r["counts"]).astype(np.int64)).cuda()
+            c = torch.from_numpy(np.ascontiguousarray(np.nan_to_num(r["counts"]).astype(np.int64))).cuda()
             dist.all_reduce(c)
             c.cpu()
     torch.cuda.synchronize()
@@ -264,8 +265,10 @@ def run_ours(args):
                 "achieved": wavefronts / (ms_reduce / 1e3) if ms_reduce > 0 else 0.0, "peak": pipe_peak,
                 "frac": (wavefronts / (ms_reduce / 1e3) / pipe_peak) if ms_reduce > 0 else 0.0,
                 "wavefronts_per_launch": wavefronts / max(1, launches), "sm_mhz": sm_clock,
-                "note": "design wavefronts of the kernel (entry broadcast + fp64 read-modify-write), label loads excluded; "
-                        "ncu l1tex__throughput for the same launch is 98.3 %"}
+                "note": "design wavefronts of the kernel (entry broadcast + fp64 read-modify-write), label loads excluded"
+                        + ("; ncu l1tex__throughput for the same launch is 98.3 %" if args.workload == "config2" else
+                           "; ncu l1tex__throughput: 96 % at K = 50 (config 3), 38-64 % at K = 120 where 7 warps/SM leave "
+                           "the kernel latency-bound (profiles/NOTES_r1.md)")}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -276,8 +279,8 @@ def run_ours(args):
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "bytes_per_launch": bytes_reduce / max(1, launches), "ms_per_launch": ms_reduce / max(1, launches),
             "launches": launches, "binding_unit": pipe,
-            "note": "lane = replicate batching makes the kernel shared-memory-pipe bound, not HBM bound (DESIGN.md section 3): "
-                    "ncu l1tex__throughput 98.7 % (profiles/r1_final_config2_raw.csv)",
+            "note": "lane = replicate batching makes the kernel shared-memory-pipe bound, not HBM bound (DESIGN.md section 3)"
+                    + (": ncu l1tex__throughput 98.3 % (profiles/r1_final_config2_raw.csv)" if args.workload == "config2" else ""),
             "unbatched_equivalent_gbs": (12.0 * prob.nnz * prob.n_conditions) * (world * iters * args.steps) / (ms_reduce / 1e3) / 1e9 if ms_reduce > 0 else None,
         }
         shares = {k: sum(s[k] for s in stats_acc) for k in ("ms_labels", "ms_reduce", "ms_score", "ms_device")}
@@ -293,7 +296,8 @@ def run_ours(args):
             "config": workload_config(args.workload, prob, cfg, {
                 "iterations_per_gpu": iters, "batch": stats_acc[0]["batch_size"],
                 "l2": "working set per step (matrix + labels + group means, ~GBs) exceeds the 126 MB L2; no flush",
-                "parallelism": f"replicates sharded over {world} GPU(s), expression matrix replicated, one NCCL all-reduce of int64 counters per step"}),
+                "parallelism": f"replicates sharded over {world} GPU(s), expression matrix replicated, one NCCL all-reduce of int64 counters per step"},
+                iters=iters),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "call_ms": e2e_call_ms, "ms_upload": e2e_stats["ms_upload"],
                     "ms_device": e2e_stats["ms_device"]},
@@ -316,6 +320,7 @@ def main():
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--iterations", type=int, default=0, help="override replicates per GPU per step")
     ap.add_argument("--batch", type=int, default=0, help="replicates per device launch (0 = auto)")
+    ap.add_argument("--e2e-warmup", type=int, default=0, help="warm-up calls of the end-to-end leg (0 = max(3, --warmup))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
