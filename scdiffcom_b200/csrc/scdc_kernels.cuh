@@ -583,9 +583,32 @@ __global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int n
 // grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K*J*32*8 + 1024).
 // ------------------------------------------------------------------------------------------------------------------
 template <int J> struct LabWord;
-template <> struct LabWord<1> { typedef uint8_t type; };
+template <> struct LabWord<1> { typedef uint32_t type; };  // one label byte, zero-extended by the load itself
 template <> struct LabWord<2> { typedef uint16_t type; };
 template <> struct LabWord<4> { typedef uint32_t type; };
+
+// J label bytes of one lane. J = 1 loads the byte straight into a 32-bit register (ld.u8 zero-extends), so that no
+// masking instruction is needed before the byte is used as an accumulator row number.
+template <int J>
+__device__ __forceinline__ typename LabWord<J>::type load_labels(const uint8_t* p);
+template <>
+__device__ __forceinline__ uint32_t load_labels<1>(const uint8_t* p) {
+  uint32_t r;
+  asm("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint16_t load_labels<2>(const uint8_t* p) {
+  uint16_t r;
+  asm("ld.global.nc.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t load_labels<4>(const uint8_t* p) {
+  uint32_t r;
+  asm("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 
 template <int J, int U, bool PAIR>
 __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
@@ -603,6 +626,9 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   const int beg = colptr[g], end = colptr[g + 1];
   const int nst = (end - beg + 31) >> 5;
   const uint8_t* labbase = lab2 + (size_t)cJ * 32 * J + lane * J;
+  asm("" : "+l"(labbase));  // one opaque 64-bit value: keeps ptxas from re-adding the uniform base on every label load
+  const uint32_t ustride = (uint32_t)lab_stride;  // label address = 64-bit lane base + u32 cell * u32 stride: one IMAD.WIDE
+  char* const accb = reinterpret_cast<char*>(acc);  // J = 1: accumulator row of label l starts at byte l * 256
   // Matrix entries and the flushed means are streamed (evict-first) so that they do not push the labels out of L2.
   // The labels of the NEXT group of U entries are loaded (L2 latency) while the CURRENT group is accumulated, and the
   // entries two stages ahead are in flight from global memory: the read-modify-write chain never waits on a load.
@@ -619,7 +645,7 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   for (int u = 0; u < U; ++u) {
     const uint4 en = stage[u];
     valN[u] = entry_value(en);
-    lbN[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en.x * lab_stride);
+    lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
   }
   for (int s = 0; s < nst; ++s) {
     uint4* cur_buf = stage + (s & 1) * 32;
@@ -643,7 +669,7 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
       for (int u = 0; u < U; ++u) {
         const uint4 en = src[u];
         valN[u] = entry_value(en);
-        lbN[u] = *reinterpret_cast<const lab_t*>(labbase + (size_t)en.x * lab_stride);
+        lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
       }
       if (PAIR && J == 1) {
         // Two entries per step: both accumulators are loaded before either add. If the two labels coincide the second
@@ -652,21 +678,33 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
         // groups of four were measured no faster).
 #pragma unroll
         for (int u = 0; u < U; u += 2) {
-          const int i1 = (int)lb[u] * 32, i2 = (int)lb[u + 1] * 32;
-          const double a1 = acc[i1], a2 = acc[i2];
+          double* const p1 = reinterpret_cast<double*>(accb + (lb[u] << 8));
+          double* const p2 = reinterpret_cast<double*>(accb + (lb[u + 1] << 8));
+          const double a1 = *p1, a2 = *p2;
           const double r1 = a1 + val[u];
-          const double r2 = ((i1 == i2) ? r1 : a2) + val[u + 1];
-          acc[i1] = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
-          acc[i2] = r2;
+          const double r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
+          *p1 = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
+          *p2 = r2;
         }
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          double cur[J];
+          if (J == 1) {
+            double* const p1 = reinterpret_cast<double*>(accb + (lb[u] << 8));
+            *p1 = *p1 + val[u];
+          } else {
+            // row (label, j) starts at byte (label * J + j) * 256: one byte extract (PRMT) + one multiply-add per row,
+            // the j * 256 part folds into the LDS / STS immediate
+            double* row[J];
+            double cur[J];
 #pragma unroll
-          for (int j = 0; j < J; ++j) cur[j] = acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32];
+            for (int j = 0; j < J; ++j)
+              row[j] = reinterpret_cast<double*>(accb + __byte_perm((uint32_t)lb[u], 0u, 0x4440u + j) * (J * 256u) + j * 256);
 #pragma unroll
-          for (int j = 0; j < J; ++j) acc[((int)((lb[u] >> (8 * j)) & 0xff) * J + j) * 32] = cur[j] + val[u];
+            for (int j = 0; j < J; ++j) cur[j] = *row[j];
+#pragma unroll
+            for (int j = 0; j < J; ++j) *row[j] = cur[j] + val[u];
+          }
         }
       }
     }
