@@ -982,15 +982,21 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
   return r;
 }
 
+// x == +0.0, or 2^-930 <= x < 2^930: the inputs for which x * rsqrt.approx(x) is a 2^-20-accurate sqrt(x). One unsigned
+// compare of the high word: negative numbers, NaN, +inf, denormals and the far tails fall outside and take the exact path.
+__device__ __forceinline__ bool de_fast_range(double x) {
+  const uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+  return (hi - 0x05D00000u) < 0x74400000u || (hi | lo) == 0u;  // exponent field in [1023 - 930, 1023 + 930)
+}
+
 // exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0
 __device__ __forceinline__ bool de_exceeds(double x1, double x0, double aob) {
-  const double s1 = (x1 == 0.0) ? 0.0 : x1 * rsqrt_approx(x1);
-  const double s0 = (x0 == 0.0) ? 0.0 : x0 * rsqrt_approx(x0);
+  // fmax keeps the approximation finite at x = 0 (0 * finite = 0 = sqrt(0)); inputs in (0, 1e-300) are out of the fast range
+  const double s1 = x1 * rsqrt_approx(fmax(x1, 1e-300));
+  const double s0 = x0 * rsqrt_approx(fmax(x0, 1e-300));
   const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;  // 2^-17
-  // products far outside [1e-280, 1e280] (flush-to-zero / overflow of the approximation), NaN or negative: exact path
-  const bool in_range = (x1 == 0.0 || (x1 > 1e-280 && x1 < 1e280)) && (x0 == 0.0 || (x0 > 1e-280 && x0 < 1e280));
-  if (in_range && d - slack > aob) return true;
-  if (in_range && d + slack < aob) return false;
+  const bool yes = d - slack > aob, no = d + slack < aob;
+  if (de_fast_range(x1) && de_fast_range(x0) && (yes || no)) return yes;
   return fabs(sqrt(x1) - sqrt(x0)) >= aob;
 }
 
