@@ -238,6 +238,62 @@ static int keygen_labels(int N, int T, const uint32_t* counts, uint64_t seed, ui
   return 0;
 }
 
+/* Differential mode, random-key generator (mirrors keygen_plan2 / k_draw_labels_keys2): key words A1 / B1 / A2 / B2 of cell i
+ * = element i % 4 of Philox block (i / 4, 0x80000000 + {0,1,2,3}, replicate). Pass 1: inside cell type t the n(t, cond1) cells
+ * with the smallest (A1, B1, i) get cond' = 0, the others 1. Pass 2: inside {cond' = c} the cells sorted by (A2, B2, i)
+ * receive the cell types 0 x n(0, c), 1 x n(1, c), ... */
+static int keygen2_applies(int N, int T, int max_nt, int max_nc) {
+  if (T < 2 || max_nt > 60000) return 0;
+  int NB1 = 32;
+  while (NB1 < 2048 && NB1 * 8 < max_nt) NB1 <<= 1;
+  while (NB1 > 32 && (long long)T * NB1 * 2 > 65536) NB1 >>= 1;
+  const double mean1 = (double)max_nt / NB1;
+  if (mean1 > 32.0) return 0;
+  const int cap1 = (mean1 <= 8.0) ? 64 : 128;
+  int NB2 = 512;
+  while (NB2 < 16384 && NB2 * 8 < max_nc) NB2 <<= 1;
+  const double mean2 = (double)max_nc / NB2;
+  if (mean2 > 32.0) return 0;
+  const int cap2 = (mean2 <= 8.0) ? 64 : 128;
+  const long long region1 = 2LL * T * NB1 + 8LL * T * cap1 + 4LL * 8 * T;
+  const long long region2 = 4LL * (NB2 + 1) + 4LL * NB2 / 32 + 8LL * (T - 1) * cap2 + 4LL * 8 * T + 256;
+  const long long smem = 4LL * ((N + 31) / 32) + (region1 > region2 ? region1 : region2) + 256;
+  return smem <= 200 * 1024;
+}
+static void key_words(uint32_t i, uint32_t stream, uint64_t seed, uint64_t rep, uint32_t* a, uint32_t* b) {
+  uint32_t wa[4], wb[4];
+  philox4x32_10(i >> 2, 0x80000000u + stream, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), wa);
+  philox4x32_10(i >> 2, 0x80000001u + stream, (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), wb);
+  *a = wa[i & 3]; *b = wb[i & 3];
+}
+static int keygen2_labels(int N, int T, const int32_t* ct_code, const uint32_t* counts /*[2][T]*/, uint64_t seed, uint64_t rep,
+                          uint8_t* cond_out, uint8_t* ct_out) {
+  keyrec* rec = (keyrec*)malloc(sizeof(keyrec) * (size_t)(N > 0 ? N : 1));
+  if (!rec) return 1;
+  for (int t = 0; t < T; ++t) { /* pass 1 */
+    int m = 0;
+    for (int i = 0; i < N; ++i)
+      if (ct_code[i] == t) { key_words((uint32_t)i, 0u, seed, rep, &rec[m].a, &rec[m].b); rec[m].i = (uint32_t)i; ++m; }
+    qsort(rec, (size_t)m, sizeof(keyrec), keyrec_cmp);
+    for (int k = 0; k < m; ++k) cond_out[rec[k].i] = (uint8_t)((uint32_t)k < counts[t] ? 0 : 1);
+  }
+  for (int c = 0; c < 2; ++c) { /* pass 2 */
+    int m = 0;
+    for (int i = 0; i < N; ++i)
+      if (cond_out[i] == c) { key_words((uint32_t)i, 2u, seed, rep, &rec[m].a, &rec[m].b); rec[m].i = (uint32_t)i; ++m; }
+    qsort(rec, (size_t)m, sizeof(keyrec), keyrec_cmp);
+    int pos = 0;
+    for (int t = 0; t < T; ++t)
+      for (uint32_t k = 0; k < counts[(size_t)c * T + t] && pos < m; ++k) ct_out[rec[pos++].i] = (uint8_t)t;
+  }
+  free(rec);
+  return 0;
+}
+static int urn_forced(void) { /* SCDC_URN_LABELS=1 selects the sequential urn generator on both sides */
+  const char* e = getenv("SCDC_URN_LABELS");
+  return e && *e && atoi(e) != 0;
+}
+
 int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int32_t* cond_code, uint64_t seed,
                          int64_t perm_offset, int64_t n, uint8_t* cond_out, uint8_t* ct_out) {
   uint32_t* base = (uint32_t*)calloc((size_t)2 * T, sizeof(uint32_t));
@@ -246,7 +302,23 @@ int oracle_philox_labels(int N, int T, int C, const int32_t* ct_code, const int3
   int32_t* visit = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
   if (!base || !remc || !urn || !visit) return 1;
   for (int i = 0; i < N; ++i) ++base[(size_t)((C == 2) ? cond_code[i] : 0) * T + ct_code[i]];
-  if (keygen_applies(N, T, C)) {
+  if (C == 2 && !urn_forced()) {
+    int max_nt = 0, max_nc = 0;
+    for (int t = 0; t < T; ++t) if ((int)(base[t] + base[(size_t)T + t]) > max_nt) max_nt = (int)(base[t] + base[(size_t)T + t]);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t n_c = 0;
+      for (int t = 0; t < T; ++t) n_c += base[(size_t)c * T + t];
+      if ((int)n_c > max_nc) max_nc = (int)n_c;
+    }
+    if (keygen2_applies(N, T, max_nt, max_nc)) {
+      int rc = 0;
+      for (int64_t q = 0; q < n && !rc; ++q)
+        rc = keygen2_labels(N, T, ct_code, base, seed, (uint64_t)(perm_offset + q), cond_out + (size_t)q * N, ct_out + (size_t)q * N);
+      free(base); free(remc); free(urn); free(visit);
+      return rc;
+    }
+  }
+  if (keygen_applies(N, T, C) && !urn_forced()) {
     int rc = 0;
     for (int64_t q = 0; q < n && !rc; ++q)
       rc = keygen_labels(N, T, base, seed, (uint64_t)(perm_offset + q), ct_out + (size_t)q * N);

@@ -219,6 +219,7 @@ struct scdc_handle {
   size_t mem_total = 0;
   // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
   std::vector<int> sub_gene_h, gene_nnz_h;
+  int max_nt = 0, max_nc = 0;  // largest cell type / largest condition (cells): inputs of keygen_plan2
   int n_active = 0;        // genes referenced by the installed rows (gene_order holds them, heaviest first)
   size_t nnz_active = 0;
   // labels of super-batch 0 drawn ahead of scdc_run (one-shot path: K1 overlaps the H2D of the matrix)
@@ -564,6 +565,12 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     }
     std::vector<double> ngd(K);
     for (int k = 0; k < K; ++k) ngd[k] = (double)ng[k];
+    for (int t = 0; t < T; ++t) h->max_nt = std::max(h->max_nt, (int)(ng[t] + (C == 2 ? ng[(size_t)T + t] : 0u)));
+    for (int c = 0; c < C; ++c) {
+      uint32_t n_c = 0;
+      for (int t = 0; t < T; ++t) n_c += ng[(size_t)c * T + t];
+      h->max_nc = std::max(h->max_nc, (int)n_c);
+    }
     // K1 visit order: differential mode walks the cells grouped by cell type (stable), detection mode in cell order
     std::vector<int> visit, ct_seg;
     if (C == 2) {
@@ -706,6 +713,44 @@ cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, 
 cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
                         uint32_t* bits1, uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
   const int T = h->T;
+  const scdc::KeygenPlan2 kp2 = scdc::keygen_plan2(h->N, T, h->max_nt, h->max_nc);
+  if (h->C == 2 && kp2.ok && !env_int("SCDC_URN_LABELS", 0)) {
+    auto kern = scdc::k_draw_labels_keys2;
+    cudaError_t e = cudaSuccess;
+    if (kp2.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp2.smem);
+    if (e != cudaSuccess) return e;
+    if (!h->keyfail.p) {
+      e = h->keyfail.alloc(1);
+      if (e == cudaSuccess) e = cudaMemsetAsync(h->keyfail.p, 0, sizeof(int), g_alloc_async ? g_alloc_stream : s);
+      if (e != cudaSuccess) return e;
+    }
+    const bool dbg = dbg_ct || dbg_cond;
+    uint8_t* out = nullptr;
+    if (!dbg) {
+      e = h->label_tmp.ensure((size_t)h->N * B);
+      if (e != cudaSuccess) return e;
+      out = h->label_tmp.p;
+    }
+    if (s != g_alloc_stream && g_alloc_async) {  // buffers are allocated in the order of the allocation stream
+      cudaEvent_t dep;
+      e = cudaEventCreateWithFlags(&dep, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      cudaError_t e1 = cudaEventRecord(dep, g_alloc_stream), e2 = cudaStreamWaitEvent(s, dep, 0);
+      cudaEventDestroy(dep);
+      if (e1 != cudaSuccess) return e1;
+      if (e2 != cudaSuccess) return e2;
+    }
+    kern<<<B, 512, kp2.smem, s>>>(h->N, T, h->ct.p, h->expect.p, seed, perm0, kp2.NB1, kp2.cap1, kp2.NB2, kp2.cap2, out,
+                                  dbg_cond, dbg_ct, h->keyfail.p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || dbg) return e;
+    for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks + pass-1 condition bits
+      dim3 grid((h->N + 127) / 128, Bb / 128);
+      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N, T,
+                                                   bits1 + (size_t)b0 / 32 * h->N);
+    }
+    return cudaGetLastError();
+  }
   const scdc::KeygenPlan kp = scdc::keygen_plan(h->N, T, h->C);
   if (kp.ok && !env_int("SCDC_URN_LABELS", 0)) {
     auto kern = scdc::k_draw_labels_keys;
@@ -737,7 +782,7 @@ cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t p
     if (e != cudaSuccess || dbg_ct) return e;
     for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks of the reduction
       dim3 grid((h->N + 127) / 128, Bb / 128);
-      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N);
+      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N, 0, nullptr);
     }
     return cudaGetLastError();
   }

@@ -5,6 +5,7 @@
 //   K1u  k_pack_uploaded /    validation mode: re-layout and check uploaded label matrices
 //        k_check_uploaded
 //   K2a  k_pass1_cond         differential pass 1 (conditions shuffled inside fixed cell types): register accumulators
+//   K1k2 k_draw_labels_keys2 differential-mode random-key shuffles (both passes), one block per replicate
 //   K2b  k_scatter<J,U,PAIR>  general segmented sum over CSC, lane = replicate, shared-memory accumulators
 //                             (replaces DelayedArray::rowsum + "/ table(group)", reference R/utils_cci.R:441-462)
 //   K3   k_score_det /        gather + complex-min + score + diff + `>=` compare + counter bump, factorised per LRI
@@ -405,6 +406,336 @@ __global__ void __launch_bounds__(256) k_draw_labels_keys(int N, int T, const ui
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K1k2: differential-mode label shuffles by random keys, one thread block per replicate.
+//   pass 1  cond' = shuffle of the conditions inside every cell type (reference R/utils_permutation.R:536-541): inside
+//           cell type t the n(t, cond1) cells with the smallest keys (A1, B1, cell) get cond' = 0, the others cond' = 1;
+//   pass 2  ct' = shuffle of the cell types inside every PERMUTED condition (:552-569): inside {cells with cond' = c} the
+//           cells sorted by the keys (A2, B2, cell) receive the labels 0 x n(0, c), 1 x n(1, c), ...
+// Key words: A1 / B1 / A2 / B2 of cell i = element i % 4 of Philox block (i / 4, 0x80000000 + {0, 1, 2, 3}, replicate).
+// Both passes select rank thresholds by histogram (pass 1: T strata x NB1 bins, 16-bit counters packed in pairs, one
+// threshold per stratum; pass 2: one stratum at a time, NB2 bins, T - 1 thresholds) and rank exactly only the members of
+// the bins that contain a threshold. cond' lives in a shared-memory bitmap between the passes.
+// Output: replicate-major combined labels out[q][cell] = cond' * T + ct' (or the two debug arrays).
+// ------------------------------------------------------------------------------------------------------------------
+struct KeygenPlan2 {
+  int ok;
+  int NB1, cap1;  // pass 1: bins per cell type, members kept per threshold bin
+  int NB2, cap2;  // pass 2
+  int smem;
+};
+
+__host__ __device__ inline KeygenPlan2 keygen_plan2(int N, int T, int max_nt, int max_nc) {
+  KeygenPlan2 pl = {0, 0, 0, 0, 0, 0};
+  if (T < 2 || max_nt > 60000) return pl;  // 16-bit bin counters
+  int NB1 = 32;
+  while (NB1 < 2048 && NB1 * 8 < max_nt) NB1 <<= 1;
+  while (NB1 > 32 && (long long)T * NB1 * 2 > 65536) NB1 >>= 1;
+  const double mean1 = (double)max_nt / NB1;
+  if (mean1 > 32.0) return pl;
+  const int cap1 = (mean1 <= 8.0) ? 64 : 128;
+  int NB2 = 512;
+  while (NB2 < 16384 && NB2 * 8 < max_nc) NB2 <<= 1;
+  const double mean2 = (double)max_nc / NB2;
+  if (mean2 > 32.0) return pl;
+  const int cap2 = (mean2 <= 8.0) ? 64 : 128;
+  const long long region1 = 2LL * T * NB1 + 8LL * T * cap1 + 4LL * 8 * T;
+  const long long region2 = 4LL * (NB2 + 1) + 4LL * NB2 / 32 + 8LL * (T - 1) * cap2 + 4LL * 8 * T + 256;
+  const long long smem = 4LL * ((N + 31) / 32) + (region1 > region2 ? region1 : region2) + 256;
+  if (smem > 200 * 1024) return pl;
+  pl.ok = 1; pl.NB1 = NB1; pl.cap1 = cap1; pl.NB2 = NB2; pl.cap2 = cap2; pl.smem = (int)smem;
+  return pl;
+}
+
+// key order with explicit stream numbers: (a, b, cell), b evaluated only on a tie of a
+__device__ __forceinline__ bool keygen_less_s(uint32_t ax, uint32_t x, uint32_t ay, uint32_t y, uint32_t sb, uint32_t r_lo,
+                                              uint32_t r_hi, uint32_t k0, uint32_t k1) {
+  if (ax != ay) return ax < ay;
+  const uint32_t bx = keygen_word(x, sb, r_lo, r_hi, k0, k1), by = keygen_word(y, sb, r_lo, r_hi, k0, k1);
+  if (bx != by) return bx < by;
+  return x < y;
+}
+
+__global__ void __launch_bounds__(512) k_draw_labels_keys2(int N, int T, const uint8_t* __restrict__ ct,
+                                                           const uint32_t* __restrict__ ngroup_u /*[2][T]*/, uint64_t seed,
+                                                           int64_t perm0, int NB1, int cap1, int NB2, int cap2,
+                                                           uint8_t* __restrict__ out, uint8_t* __restrict__ dbg_cond,
+                                                           uint8_t* __restrict__ dbg_ct, int* __restrict__ fail) {
+  extern __shared__ uint32_t sm_k[];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int q = blockIdx.x;
+  const uint64_t rep = (uint64_t)(perm0 + q);
+  const uint32_t r_lo = (uint32_t)rep, r_hi = (uint32_t)(rep >> 32), k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const int nwords = (N + 31) / 32;
+  uint32_t* bitmap = sm_k;            // [nwords] cond' of every cell
+  uint32_t* region = bitmap + nwords;
+  for (int w = tid; w < nwords; w += nthr) bitmap[w] = 0;
+  // =========================== pass 1: conditions inside every cell type ===========================
+  {
+    int lg = 0;
+    while ((1 << lg) < NB1) ++lg;
+    const int shift = 32 - lg;
+    uint32_t* hist = region;                  // [T * NB1 / 2] pairs of 16-bit counters
+    uint32_t* tb = hist + T * NB1 / 2;        // [T] bin of the threshold (0xffffffff: every cell keeps cond' = 0)
+    uint32_t* tq = tb + T;                    // [T] rank of the threshold inside its bin
+    uint32_t* lcnt = tq + T;                  // [T]
+    uint32_t* thrA = lcnt + T;                // [T] threshold key
+    uint32_t* thrB = thrA + T;
+    uint32_t* thrI = thrB + T;
+    uint32_t* lkey = thrI + T + 2 * T;        // [T][cap1]   (2 T words of slack keep the layout equal to the plan's size)
+    uint32_t* lidx = lkey + T * cap1;         // [T][cap1]
+    for (int b = tid; b < T * NB1 / 2; b += nthr) hist[b] = 0;
+    for (int t = tid; t < T; t += nthr) lcnt[t] = 0;
+    __syncthreads();
+    for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {
+      uint32_t w[4];
+      philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i4 + k < N) {
+          const uint32_t idx = (uint32_t)ct[i4 + k] * NB1 + (w[k] >> shift);
+          atomicAdd(&hist[idx >> 1], 1u << ((idx & 1) * 16));
+        }
+    }
+    __syncthreads();
+    // thresholds: one warp per cell type; theta_t = the cell of rank n(t, cond1) = first cell that gets cond' = 1
+    for (int t = warp; t < T; t += nwarp) {
+      const uint32_t r = ngroup_u[t], n_t = ngroup_u[t] + ngroup_u[T + t];
+      const int per = NB1 / 32;
+      uint32_t loc = 0;
+      for (int k = 0; k < per; ++k) {
+        const uint32_t idx = (uint32_t)t * NB1 + lane * per + k;
+        loc += (hist[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
+      }
+      uint32_t inc = loc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      if (lane == 0) {
+        if (total != n_t) atomicExch(fail, 3);  // a 16-bit bin counter overflowed
+        if (r >= n_t) tb[t] = 0xffffffffu;
+      }
+      const uint32_t exc = inc - loc;
+      if (r < n_t && exc <= r && r < inc) {
+        uint32_t run = exc;
+        for (int k = 0; k < per; ++k) {
+          const uint32_t idx = (uint32_t)t * NB1 + lane * per + k;
+          const uint32_t c = (hist[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
+          if (r < run + c) { tb[t] = lane * per + k; tq[t] = r - run; break; }
+          run += c;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {  // members of the threshold bins
+      uint32_t w[4];
+      philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i4 + k >= N) continue;
+        const uint32_t t = ct[i4 + k];
+        if ((w[k] >> shift) != tb[t]) continue;
+        const uint32_t pos = atomicAdd(&lcnt[t], 1u);
+        if (pos < (uint32_t)cap1) { lkey[t * cap1 + pos] = w[k]; lidx[t * cap1 + pos] = (uint32_t)(i4 + k); }
+        else atomicExch(fail, 1);
+      }
+    }
+    __syncthreads();
+    for (int pair = tid; pair < T * cap1; pair += nthr) {
+      const int t = pair / cap1, x = pair % cap1;
+      const int mj = min((int)lcnt[t], cap1);
+      if (x >= mj || tb[t] == 0xffffffffu) continue;
+      const uint32_t ax = lkey[t * cap1 + x], ix = lidx[t * cap1 + x];
+      uint32_t less = 0;
+      for (int y = 0; y < mj; ++y)
+        if (y != x && keygen_less_s(lkey[t * cap1 + y], lidx[t * cap1 + y], ax, ix, 1u, r_lo, r_hi, k0, k1)) ++less;
+      if (less == tq[t]) {
+        thrA[t] = ax;
+        thrI[t] = ix;
+        thrB[t] = keygen_word(ix, 1u, r_lo, r_hi, k0, k1);
+      }
+    }
+    __syncthreads();
+    for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {  // cond' = (key >= theta of the cell's type)
+      uint32_t w[4];
+      philox4x32_10((uint32_t)i4 >> 2, 0x80000000u, r_lo, r_hi, k0, k1, w);
+      uint32_t nib = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i4 + k >= N) continue;
+        const uint32_t i = (uint32_t)(i4 + k), t = ct[i], a = w[k], bin = a >> shift, tbin = tb[t];
+        bool one;
+        if (tbin == 0xffffffffu) one = false;
+        else if (bin != tbin) one = bin > tbin;
+        else if (a != thrA[t]) one = a > thrA[t];
+        else if (i == thrI[t]) one = true;
+        else {
+          const uint32_t b = keygen_word(i, 1u, r_lo, r_hi, k0, k1);
+          one = (b != thrB[t]) ? (b > thrB[t]) : (i > thrI[t]);
+        }
+        nib |= (one ? 1u : 0u) << k;
+      }
+      if (nib) atomicOr(&bitmap[i4 >> 5], nib << (i4 & 31));
+    }
+    __syncthreads();
+  }
+  // =========================== pass 2: cell types inside every permuted condition ===========================
+  {
+    const int m = T - 1;
+    int lg = 0;
+    while ((1 << lg) < NB2) ++lg;
+    const int shift = 32 - lg;
+    uint32_t* hist = region;                     // [NB2 + 1] counts, then exclusive prefix
+    uint32_t* mark = hist + NB2 + 1;             // [NB2 / 32] bitmap of threshold bins
+    uint32_t* tbin = mark + NB2 / 32;            // [m]
+    uint32_t* tq = tbin + m;
+    uint32_t* lcnt = tq + m;
+    uint32_t* thrA = lcnt + m;
+    uint32_t* thrB = thrA + m;
+    uint32_t* thrI = thrB + m;
+    uint32_t* wsum = thrI + m;                   // [32]
+    uint32_t* lkey = wsum + 32;                  // [m][cap2]
+    uint32_t* lidx = lkey + m * cap2;
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t* cnt = ngroup_u + c * T;    // n(t, c), t = 0..T-1
+      for (int b = tid; b <= NB2; b += nthr) hist[b] = 0;
+      for (int b = tid; b < NB2 / 32; b += nthr) mark[b] = 0;
+      for (int j = tid; j < m; j += nthr) lcnt[j] = 0;
+      __syncthreads();
+      for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {
+        const uint32_t member = ((c ? bitmap[i4 >> 5] : ~bitmap[i4 >> 5]) >> (i4 & 31)) & 0xfu;
+        if (!member) continue;
+        uint32_t w[4];
+        philox4x32_10((uint32_t)i4 >> 2, 0x80000002u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i4 + k < N && ((member >> k) & 1u)) atomicAdd(&hist[w[k] >> shift], 1u);
+      }
+      __syncthreads();
+      {  // exclusive scan of the NB2 bins (NB2 / nthr consecutive bins per thread)
+        const int per = NB2 / nthr;
+        uint32_t loc = 0;
+        for (int k = 0; k < per; ++k) loc += hist[tid * per + k];
+        uint32_t inc = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (tid < 32) {
+          uint32_t v = (tid < nwarp) ? wsum[tid] : 0, iv = v;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, iv, d);
+            if (tid >= d) iv += u;
+          }
+          wsum[tid] = iv - v;
+        }
+        __syncthreads();
+        uint32_t run = wsum[warp] + inc - loc;
+        for (int k = 0; k < per; ++k) {
+          const uint32_t cc = hist[tid * per + k];
+          hist[tid * per + k] = run;
+          run += cc;
+        }
+        if (tid == nthr - 1) hist[NB2] = run;
+      }
+      __syncthreads();
+      for (int j = tid; j < m; j += nthr) {  // rank n(0,c) + .. + n(j,c) -> (bin, rank inside the bin)
+        uint32_t r = 0;
+        for (int k = 0; k <= j; ++k) r += cnt[k];
+        int lo = 0, hi = NB2;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (hist[mid + 1] > r) hi = mid; else lo = mid + 1;
+        }
+        tbin[j] = (uint32_t)lo;  // lo == NB2: rank beyond the stratum (trailing empty labels), a threshold no key reaches
+        tq[j] = (lo < NB2) ? r - hist[lo] : 0u;
+        if (lo < NB2) atomicOr(&mark[lo >> 5], 1u << (lo & 31));
+      }
+      __syncthreads();
+      for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {  // members of the threshold bins
+        const uint32_t member = ((c ? bitmap[i4 >> 5] : ~bitmap[i4 >> 5]) >> (i4 & 31)) & 0xfu;
+        if (!member) continue;
+        uint32_t w[4];
+        philox4x32_10((uint32_t)i4 >> 2, 0x80000002u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (i4 + k >= N || !((member >> k) & 1u)) continue;
+          const uint32_t bin = w[k] >> shift;
+          if (!((mark[bin >> 5] >> (bin & 31)) & 1u)) continue;
+          int lo = 0, hi = m;  // first threshold with tbin >= bin
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tbin[mid] >= bin) hi = mid; else lo = mid + 1;
+          }
+          for (int j = lo; j < m && tbin[j] == bin; ++j) {
+            const uint32_t pos = atomicAdd(&lcnt[j], 1u);
+            if (pos < (uint32_t)cap2) { lkey[j * cap2 + pos] = w[k]; lidx[j * cap2 + pos] = (uint32_t)(i4 + k); }
+            else atomicExch(fail, 1);
+          }
+        }
+      }
+      __syncthreads();
+      for (int pair = tid; pair < m * cap2; pair += nthr) {
+        const int j = pair / cap2, x = pair % cap2;
+        const int mj = min((int)lcnt[j], cap2);
+        if (x >= mj) continue;
+        const uint32_t ax = lkey[j * cap2 + x], ix = lidx[j * cap2 + x];
+        uint32_t less = 0;
+        for (int y = 0; y < mj; ++y)
+          if (y != x && keygen_less_s(lkey[j * cap2 + y], lidx[j * cap2 + y], ax, ix, 3u, r_lo, r_hi, k0, k1)) ++less;
+        if (less == tq[j]) {
+          thrA[j] = ax;
+          thrI[j] = ix;
+          thrB[j] = keygen_word(ix, 3u, r_lo, r_hi, k0, k1);
+        }
+      }
+      __syncthreads();
+      for (int i4 = tid * 4; i4 < N; i4 += nthr * 4) {  // ct' = number of thresholds <= key
+        const uint32_t member = ((c ? bitmap[i4 >> 5] : ~bitmap[i4 >> 5]) >> (i4 & 31)) & 0xfu;
+        if (!member) continue;
+        uint32_t w[4];
+        philox4x32_10((uint32_t)i4 >> 2, 0x80000002u, r_lo, r_hi, k0, k1, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (i4 + k >= N || !((member >> k) & 1u)) continue;
+          const uint32_t i = (uint32_t)(i4 + k), a = w[k], bin = a >> shift;
+          int lo = 0, hi = m;
+          if (!((mark[bin >> 5] >> (bin & 31)) & 1u)) {
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (tbin[mid] < bin) lo = mid + 1; else hi = mid;
+            }
+          } else {
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              bool thr_le;  // theta_mid <= key_i
+              if (tbin[mid] != bin) thr_le = tbin[mid] < bin;
+              else if (thrA[mid] != a) thr_le = thrA[mid] < a;
+              else if (thrI[mid] == i) thr_le = true;
+              else {
+                const uint32_t b = keygen_word(i, 3u, r_lo, r_hi, k0, k1);
+                thr_le = (thrB[mid] != b) ? (thrB[mid] < b) : (thrI[mid] < i);
+              }
+              if (thr_le) lo = mid + 1; else hi = mid;
+            }
+          }
+          if (out) out[(size_t)q * N + i] = (uint8_t)(c * T + lo);
+          if (dbg_ct) dbg_ct[(size_t)q * N + i] = (uint8_t)lo;
+          if (dbg_cond) dbg_cond[(size_t)q * N + i] = (uint8_t)c;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K1u: validation mode. up_ct / up_cond are replicate-major [nb][N]; writes the same device layouts as K1.
 // Replicates q >= nb (padding) get the original labels (results for them are never counted).
 // grid = (ceil(N/32), Bpad/32), block = (32, 32): threadIdx.x = replicate in word, threadIdx.y = cell in tile.
@@ -445,8 +776,9 @@ __global__ void k_pack_uploaded(int N, int T, int C, int nb, int Bpad, int J, co
 // Re-layout of the random-key generator's replicate-major labels in[rep][cell] (detection mode) into one reduction batch
 // block out[cell][Bb] (J labels of a lane adjacent). Tile = 128 replicates x 128 cells through shared memory: 128-byte
 // coalesced reads of a replicate's cells, 128-byte coalesced writes of a cell's replicates. grid = (ceil(N/128), Bb/128).
+// T_bits > 0 (differential mode, labels = cond' * T + ct'): also writes the pass-1 condition bits bits1[cell][Bb / 32].
 __global__ void __launch_bounds__(256) k_relayout_labels(int N, int Bb, int J, const uint8_t* __restrict__ in,
-                                                         uint8_t* __restrict__ out) {
+                                                         uint8_t* __restrict__ out, int T_bits, uint32_t* __restrict__ bits1) {
   __shared__ __align__(16) uint8_t tile[128][132];
   const int cell0 = blockIdx.x * 128, rep0 = blockIdx.y * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -474,6 +806,16 @@ __global__ void __launch_bounds__(256) k_relayout_labels(int N, int Bb, int J, c
       packed |= (uint32_t)tile[rep][c] << (8 * k);
     }
     *reinterpret_cast<uint32_t*>(out + (size_t)(cell0 + c) * Bb + rep0 + wd * 4) = packed;
+  }
+  if (T_bits > 0) {
+    for (int item = threadIdx.x; item < 128 * 4; item += 256) {
+      const int c = item >> 2, w = item & 3;
+      if (cell0 + c >= N) continue;
+      uint32_t word = 0;
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b) word |= (tile[w * 32 + b][c] >= T_bits ? 1u : 0u) << b;
+      bits1[(size_t)(cell0 + c) * (Bb / 32) + (rep0 >> 5) + w] = word;
+    }
   }
 }
 

@@ -72,8 +72,12 @@ def test_group_means_bit_exact(liver_cases, mode):
     assert np.array_equal(dr, oracle_c.group_means(prob, grp, detection=True))
 
 
+@pytest.mark.parametrize("urn", [0, 1])
 @pytest.mark.parametrize("mode", ["cond", "nocond"])
-def test_device_philox_labels_match_cpu_restatement(liver_cases, mode):
+def test_device_philox_labels_match_cpu_restatement(liver_cases, mode, urn, monkeypatch):
+    """urn = 0: the random-key generators (K1k / K1k2); urn = 1: the sequential urn generator (SCDC_URN_LABELS=1 selects
+    it in the library and in the oracle's restatement alike)."""
+    monkeypatch.setenv("SCDC_URN_LABELS", str(urn))
     prob = liver_cases[mode]["prob"]
     with Engine(prob) as eng:
         cond, ct = eng.draw_labels(200, seed=1234, perm_offset=1000)
@@ -89,7 +93,9 @@ def test_device_philox_labels_match_cpu_restatement(liver_cases, mode):
     dict(n_cells=6000, n_genes=20, n_celltypes=100, n_conditions=1, n_lri=30, seed=13, min_group=10),   # NG = 16
     dict(n_cells=9000, n_genes=20, n_celltypes=200, n_conditions=1, n_lri=30, seed=14, min_group=10),   # NG = 32
 ])
-def test_device_philox_labels_match_cpu_restatement_all_urn_widths(kw):
+@pytest.mark.parametrize("urn", [0, 1])
+def test_device_philox_labels_match_cpu_restatement_all_urn_widths(kw, urn, monkeypatch):
+    monkeypatch.setenv("SCDC_URN_LABELS", str(urn))
     prob, ai, simple, mask = synthetic.make_problem(kw)
     with Engine(prob) as eng:
         cond, ct = eng.draw_labels(40, seed=kw["seed"], perm_offset=2**33 + 5)   # 64-bit replicate index
@@ -195,6 +201,41 @@ def test_device_shuffles_are_uniform(liver_cases):
     expect = (nt * (nt - 1)).sum() / (N * (N - 1))
     same = (ct[:, :-1] == ct[:, 1:]).mean()
     assert abs(same - expect) < 5 * np.sqrt(expect * (1 - expect) / (n * (N - 1)))
+
+
+def test_device_shuffles_are_uniform_differential(liver_cases):
+    """Differential mode (random keys, two passes): cond' is a uniform shuffle inside every cell type, ct' a uniform
+    shuffle inside every permuted condition; both keep n(cell type, condition)."""
+    prob = liver_cases["cond"]["prob"]
+    n = 3000
+    with Engine(prob) as eng:
+        cond, ct = eng.draw_labels(n, seed=123)
+    T, N = prob.n_celltypes, prob.n_cells
+    ct0, cd0 = np.asarray(prob.ct_code), np.asarray(prob.cond_code)
+    base = np.zeros((2, T), np.int64)
+    np.add.at(base, (cd0, ct0), 1)
+    for q in (0, 1, n - 1):          # group sizes of both passes are preserved
+        p1 = np.zeros((2, T), np.int64); np.add.at(p1, (cond[q], ct0), 1)
+        p2 = np.zeros((2, T), np.int64); np.add.at(p2, (cond[q], ct[q]), 1)
+        assert np.array_equal(p1, base) and np.array_equal(p2, base)
+    # pass 1: P(cond' = 1 | cell of type t) = n(t, cond2) / n_t for every cell
+    p1 = (base[1] / base.sum(0))[ct0]                       # [N]
+    freq = cond.mean(0)
+    z = (freq - p1) / np.sqrt(p1 * (1 - p1) / n)
+    assert np.abs(z).max() < 5.5 and abs((z ** 2).sum() - N) < 6 * np.sqrt(2 * N)
+    # pass 2: P(ct' = t | cond' = c) = n(t, c) / n_c, pooled over cells
+    for c in (0, 1):
+        sel = cond == c
+        obs = np.array([(ct[sel] == t).sum() for t in range(T)])
+        exp = base[c] / base[c].sum() * sel.sum()
+        assert np.allclose(obs, exp)                        # exact by construction (every replicate keeps the counts)
+    # ... and per cell: chi-square of the per-cell ct' frequencies against the mixture over cond'
+    pc = np.stack([1 - p1, p1], axis=1)                     # [N, 2] P(cond' = c) for the cell
+    pt = pc @ (base / base.sum(1, keepdims=True))           # [N, T]
+    obs = np.stack([(ct == t).sum(0) for t in range(T)], axis=1)
+    chi2 = ((obs - n * pt) ** 2 / (n * pt)).sum()
+    dof = N * (T - 1)
+    assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
 
 
 def test_in_library_multi_gpu_equals_single_gpu(liver_cases):
