@@ -1170,9 +1170,13 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     if (C == 2) {
       const int nWC = B / 128, W = 8;
       const long long tasks = (long long)h->n_active * nWC;
-      scdc::k_pass1_cond<<<(unsigned)((tasks + W - 1) / W), W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p,
-                                                                           h->values_s.p, bits1_b, Bw, h->ngroup.p,
-                                                                           h->gene_order.p, M1b);
+      const unsigned grid1 = (unsigned)((tasks + W - 1) / W);
+      if (env_int("SCDC_U1", 4) == 4)  // 80 registers, 3 blocks / SM; U = 8 (144 registers, 1 block) measured slower
+        scdc::k_pass1_cond<4><<<grid1, W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
+                                                       h->ngroup.p, h->gene_order.p, M1b);
+      else
+        scdc::k_pass1_cond<8><<<grid1, W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
+                                                       h->ngroup.p, h->gene_order.p, M1b);
       CU(cudaGetLastError());
       ++launches; ++reduce_launches;
     }

@@ -864,18 +864,20 @@ __device__ __forceinline__ double entry_value(const uint4& e) {
 // exactly acc + v (the product is exact, one rounding) and v * 0.0 + acc leaves acc unchanged, so the result is bit-identical
 // to the branchy form, in 5 instructions instead of the 7 (two adds + four selects + test) the compiler emits for it.
 __device__ __forceinline__ void sel_add(double& acc1, double& acc0, uint32_t sel, double v) {
+  // (two predicated add.f64 in inline PTX do not survive either: ptxas turns them into add + FSEL pairs)
   const int hi1 = sel ? 0x3FF00000 : 0;
   const double b1 = __hiloint2double(hi1, 0), b0 = __hiloint2double(hi1 ^ 0x3FF00000, 0);
   acc1 = fma(v, b1, acc1);
   acc0 = fma(v, b0, acc0);
 }
 
+template <int U>
 __global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
                                                     const int* __restrict__ rowidx_s, const double* __restrict__ values_s,
                                                     const uint32_t* __restrict__ bits1, int Bw,
                                                     const double* __restrict__ ngroup, const int* __restrict__ gene_order,
                                                     double* __restrict__ M1) {
-  __shared__ uint4 stage_all[8][32];
+  __shared__ uint4 stage_all[8][64];  // per warp: two buffers of 32 entries
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   const long long task = (long long)blockIdx.x * W + warp;
   if (task >= (long long)nGa * nWC) return;  // nGa active genes (gene_order), G = layout stride of M1
@@ -884,34 +886,73 @@ __global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int n
   const int K = 2 * T;
   const uint32_t lane_bit = 1u << lane;
   const int* sp = segptr + (size_t)g * (T + 1);
+  const uint32_t* bitbase = bits1 + wc * 4;  // + cell * Bw: the 128 condition bits of this warp's replicates
+  asm("" : "+l"(bitbase));
+  const uint32_t ubw = (uint32_t)Bw;
+  // Same software pipeline as k_scatter: the entries two stages ahead are in flight from global memory, and the condition
+  // bits of the NEXT group of U entries (one uniform 16-byte load per entry, L2 latency) are loaded while the CURRENT
+  // group is accumulated. Padding entries are (cell 0, +0.0): bit-neutral.
   for (int t = 0; t < T; ++t) {
     const int beg = sp[t], end = sp[t + 1];
+    const int nst = (end - beg + 31) >> 5;
     double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int e0 = beg; e0 < end; e0 += 32) {
-      int e = e0 + lane;
-      int cell = 0;
-      double v = 0.0;
-      if (e < end) { cell = rowidx_s[e]; v = values_s[e]; }
+    if (nst > 0) {
+      int cell_n = 0;
+      double v_n = 0.0;
+      if (beg + lane < end) { cell_n = __ldcs(rowidx_s + beg + lane); v_n = __ldcs(values_s + beg + lane); }
+      __syncwarp();  // every lane is done with the previous segment's buffers
+      stage[lane] = pack_entry(cell_n, v_n);
+      cell_n = 0; v_n = 0.0;
+      if (beg + 32 + lane < end) { cell_n = __ldcs(rowidx_s + beg + 32 + lane); v_n = __ldcs(values_s + beg + 32 + lane); }
       __syncwarp();
-      stage[lane] = pack_entry(cell, v);
-      __syncwarp();
-      const int n = min(32, end - e0);
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        uint4 en = stage[i];
-        double val = entry_value(en);
-        uint4 w = *reinterpret_cast<const uint4*>(bits1 + (size_t)en.x * (unsigned)Bw + wc * 4);
-        uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      double valN[U];
+      uint4 bN[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sel_add(a1[j], a0[j], ww[j] & lane_bit, val);
+      for (int u = 0; u < U; ++u) {
+        const uint4 en = stage[u];
+        valN[u] = entry_value(en);
+        bN[u] = __ldg(reinterpret_cast<const uint4*>(bitbase + (uint64_t)en.x * ubw));
+      }
+      for (int s = 0; s < nst; ++s) {
+        uint4* cur_buf = stage + (s & 1) * 32;
+        uint4* nxt_buf = stage + ((s + 1) & 1) * 32;
+        __syncwarp();
+        nxt_buf[lane] = pack_entry(cell_n, v_n);
+        {
+          const int e = beg + (s + 2) * 32 + lane;
+          cell_n = 0; v_n = 0.0;
+          if (e < end) { cell_n = __ldcs(rowidx_s + e); v_n = __ldcs(values_s + e); }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int gq = 0; gq < 32 / U; ++gq) {
+          double val[U];
+          uint4 b[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) { val[u] = valN[u]; b[u] = bN[u]; }
+          const uint4* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint4 en = src[u];
+            valN[u] = entry_value(en);
+            bN[u] = __ldg(reinterpret_cast<const uint4*>(bitbase + (uint64_t)en.x * ubw));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            sel_add(a1[0], a0[0], b[u].x & lane_bit, val[u]);
+            sel_add(a1[1], a0[1], b[u].y & lane_bit, val[u]);
+            sel_add(a1[2], a0[2], b[u].z & lane_bit, val[u]);
+            sel_add(a1[3], a0[3], b[u].w & lane_bit, val[u]);
+          }
+        }
       }
     }
     const double n0 = ngroup[t], n1 = ngroup[T + t];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       size_t base = (((size_t)(wc * 4 + j) * G + g) * K) * 32 + lane;
-      M1[base + (size_t)t * 32] = a0[j] / n0;
-      M1[base + (size_t)(T + t) * 32] = a1[j] / n1;
+      __stcs(&M1[base + (size_t)t * 32], a0[j] / n0);
+      __stcs(&M1[base + (size_t)(T + t) * 32], a1[j] / n1);
     }
   }
 }
