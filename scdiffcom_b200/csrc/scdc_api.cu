@@ -243,6 +243,7 @@ constexpr int kScoreThreads = 256, kScoreRPT = 2;
 int prelaunch_labels(scdc_handle* h, const scdc_options* o);
 int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, const scdc_options* o,
                                        std::atomic<int>& genes_valid, std::atomic<bool>& matrix_done, const int& matrix_rc);
+int launch_early_scatter(scdc_handle* h, const scdc_options* o);
 
 int count_sm100_devices(std::vector<int>* ids) {
   int n = 0;
@@ -421,7 +422,17 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   CU(h->row_recv.upload(row_recv, n_rows, s));
   CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
   h->obs_na.resize((size_t)n_rows * h->ncols);
-  for (size_t i = 0; i < h->obs_na.size(); ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
+  const int n_thr = ((size_t)n_rows * h->ncols > (1u << 20)) ? 4 : 1;  // a few host threads on large tables
+  auto parallel = [&](auto&& fn) {
+    std::vector<std::thread> th;
+    for (int w = 1; w < n_thr; ++w) th.emplace_back([&fn, w]() { fn(w); });
+    fn(0);
+    for (auto& t : th) t.join();
+  };
+  parallel([&](int w) {
+    const size_t n = h->obs_na.size(), lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
+    for (size_t i = lo; i < hi; ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
+  });
   // K3 work list: rows stably sorted by LRI (counting sort), each LRI cut into slices of score_threads * kScoreRPT rows
   std::vector<int> srow(n_rows), t_lri, t_beg, t_end;
   {
@@ -460,17 +471,20 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
     const size_t n_tab = (size_t)h->L * T * h->nS;
     obs_sub.assign(n_tab, std::nan(""));
     std::vector<uint8_t> seen(n_tab, 0);
-    bool ok = true;
-    for (int r = 0; r < n_rows && ok; ++r) {
-      for (int sidx = 0; sidx < h->nS; ++sidx) {
-        const int ctx = (sidx < h->nL) ? row_emit[r] : row_recv[r];
-        const size_t k = ((size_t)row_lri[r] * T + ctx) * h->nS + sidx;
-        const double v = observed[(size_t)(3 + sidx) * n_rows + r];
-        if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
-        else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
+    std::atomic<bool> ok{true};
+    parallel([&](int w) {  // thread w owns the LRIs with lri % n_thr == w: disjoint table entries, no races
+      for (int r = 0; r < n_rows && ok.load(std::memory_order_relaxed); ++r) {
+        if (row_lri[r] % n_thr != w) continue;
+        for (int sidx = 0; sidx < h->nS; ++sidx) {
+          const int ctx = (sidx < h->nL) ? row_emit[r] : row_recv[r];
+          const size_t k = ((size_t)row_lri[r] * T + ctx) * h->nS + sidx;
+          const double v = observed[(size_t)(3 + sidx) * n_rows + r];
+          if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
+          else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
+        }
       }
-    }
-    h->fact_ok = ok && !env_int("SCDC_NO_FACT", 0);
+    });
+    h->fact_ok = ok.load() && !env_int("SCDC_NO_FACT", 0);
     if (h->fact_ok) CU(h->obs_sub.upload(obs_sub.data(), n_tab, s));
   }
   CU(h->srow.upload(srow.data(), srow.size(), s));
@@ -629,6 +643,20 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       }
     }
     pt.lap("create: enqueue uploads");
+    // Differential mode, one-shot call: the pass-2 group sums of batch 0 need only the matrix, the labels and the list of
+    // active genes. They are launched now; the pass-1 copy of the matrix and the rows are built and uploaded on the copy
+    // stream (and allocated in its order) while that kernel runs. run_device then skips batch 0's k_scatter.
+    cudaStream_t s_up = s;
+    if (o_hint && C == 2 && h->pre.valid && !o_hint->return_distributions && !env_int("SCDC_NO_EARLY_REDUCE", 0) &&
+        p->n_rows > 0) {
+      h->R = p->n_rows;
+      rc = install_active_genes(h.get(), p->n_rows, p->row_lri);
+      if (rc) return rc;
+      rc = launch_early_scatter(h.get(), o_hint);
+      if (rc) return rc;
+      if (h->pre.k2_done) s_up = h->stream_score;
+    }
+    AllocScope up_scope(s_up);
     std::vector<int> segptr;
     std::unique_ptr<int[]> rows_s;        // not value-initialised: the worker threads first-touch their own ranges
     std::unique_ptr<double[]> vals_s;
@@ -665,18 +693,20 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
         g_lo = g_hi;
       }
       for (auto& t : workers) t.join();
-      CU(h->segptr.upload(segptr.data(), segptr.size(), s));
+      CU(h->segptr.upload(segptr.data(), segptr.size(), s_up));
       pt.lap("create: pass-1 copy built");
-      CU(upload_big(h->rowidx_s, rows_s.get(), h->nnz, s));
-      CU(upload_big(h->values_s, vals_s.get(), h->nnz, s));
+      CU(upload_big(h->rowidx_s, rows_s.get(), h->nnz, s_up));
+      CU(upload_big(h->values_s, vals_s.get(), h->nnz, s_up));
     }
     pt.lap("create: pass-1 matrix copy");
     if (!rows_installed) {
-      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed);
+      // s_up != s: everything queued on the copy stream so far is covered by the event install_rows records at its end
+      rc = install_rows(h.get(), p->n_rows, p->row_lri, p->row_emit, p->row_recv, p->observed, s_up != s ? s_up : nullptr);
       if (rc) return rc;
     }
     CU(h->flag.alloc(1));
     pt.lap("create: enqueue rest");
+    if (s_up != s) CU(cudaStreamSynchronize(s_up));
     CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
     pt.lap("create: wait for H2D");
   } catch (const std::bad_alloc&) {
@@ -1007,6 +1037,28 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
   return SCDC_OK;
 }
 
+// One-shot call, differential mode: k_scatter of batch 0 over the whole (already uploaded and validated) matrix, launched
+// from scdc_create so that it runs while the host builds and uploads the pass-1 copy and the rows.
+int launch_early_scatter(scdc_handle* h, const scdc_options* o) {
+  cudaStream_t s = h->stream;
+  const int B = pick_batch(h, o);
+  const ScatterPlan pl = plan_scatter(h, B);
+  if (pl.J != h->pre.J || h->n_active == 0) return SCDC_OK;  // (cannot happen / nothing to reduce): the normal path runs
+  CU(h->M2[0].ensure((size_t)(B / 32) * h->G * h->K * 32));
+  if (!h->pre.k2_t0) { CU(cudaEventCreate(&h->pre.k2_t0)); CU(cudaEventCreate(&h->pre.k2_t1)); }
+  CU(cudaStreamWaitEvent(s, h->pre.t1, 0));  // labels of super-batch 0
+  CU(cudaEventRecord(h->pre.k2_t0, s));
+  cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s)
+                   : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s)
+                                 : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s);
+  CU(le);
+  CU(cudaEventRecord(h->pre.k2_t1, s));
+  h->pre.k2_done = true;
+  h->pre.B = B;
+  h->pre.k2_launches = 1;
+  return SCDC_OK;
+}
+
 // Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
 // h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
 int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st, cudaStream_t s) {
@@ -1025,7 +1077,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   const int64_t SB = uploaded ? B : pick_super_batch(h, o, B);
   const bool pre_ok = !uploaded && h->pre.valid && h->pre.seed == o->seed && h->pre.perm_offset == o->perm_offset &&
                       h->pre.SB == SB && h->pre.J == pl.J;
-  const bool early_k2 = pre_ok && h->pre.k2_done && h->pre.B == B && C == 1 && s == h->stream;
+  const bool early_k2 = pre_ok && h->pre.k2_done && h->pre.B == B && s == h->stream;
   h->pre.valid = false;  // consumed (or stale)
   h->pre.k2_done = false;
   const int SBw = (int)(SB / 32);
@@ -1384,10 +1436,16 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
     res->stats.kernel_launches += 1;
   }
   if (res->counts) {
-    std::vector<uint32_t> raw32(n);
-    if (n) CU(cudaMemcpy(raw32.data(), h->counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    std::vector<long long> raw(raw32.begin(), raw32.end());
-    finish_counts(h, raw, res->counts);
+    std::unique_ptr<uint32_t[]> raw32(new uint32_t[n ? n : 1]);
+    if (n) CU(cudaMemcpy(raw32.get(), h->counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const int n_thr = (n > (1u << 20)) ? 4 : 1;  // widen + NA marks, a few host threads on large tables
+    std::vector<std::thread> th;
+    for (int w = 0; w < n_thr; ++w)
+      th.emplace_back([&, w]() {
+        const size_t lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
+        for (size_t i = lo; i < hi; ++i) res->counts[i] = h->obs_na[i] ? SCDC_COUNT_NA : (uint64_t)raw32[i];
+      });
+    for (auto& t : th) t.join();
   }
   res->stats.ms_merge = now_ms() - t1;
   res->stats.ms_total = now_ms() - t0;

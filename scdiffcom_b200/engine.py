@@ -74,6 +74,7 @@ class PermutationProblem:
         self.row_recv = _arr(self.row_recv, np.int32)
         obs = np.asarray(self.observed, dtype=np.float64).reshape(self.n_rows, self.ncols)
         obs_f = np.asfortranarray(obs)
+        self.observed = obs_f     # column-major once: later calls on the same problem do not copy it again
         self._keep = [obs_f]
         p = Problem()
         p.n_cells, p.n_genes, p.n_celltypes, p.n_conditions = self.n_cells, self.n_genes, self.n_celltypes, self.n_conditions
