@@ -886,9 +886,9 @@ __global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int n
   const int K = 2 * T;
   const uint32_t lane_bit = 1u << lane;
   const int* sp = segptr + (size_t)g * (T + 1);
-  const uint32_t* bitbase = bits1 + wc * 4;  // + cell * Bw: the 128 condition bits of this warp's replicates
+  const char* bitbase = reinterpret_cast<const char*>(bits1 + wc * 4);  // + cell * Bw * 4 bytes: this warp's 128 condition bits
   asm("" : "+l"(bitbase));
-  const uint32_t ubw = (uint32_t)Bw;
+  const uint32_t ubw = (uint32_t)Bw * 4u;  // byte stride: the address is one IMAD.WIDE (u32 cell x u32 stride + 64-bit base)
   // Same software pipeline as k_scatter: the entries two stages ahead are in flight from global memory, and the condition
   // bits of the NEXT group of U entries (one uniform 16-byte load per entry, L2 latency) are loaded while the CURRENT
   // group is accumulated. Padding entries are (cell 0, +0.0): bit-neutral.
