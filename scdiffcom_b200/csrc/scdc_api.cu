@@ -1143,6 +1143,14 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(cudaEventRecord(m_ready[0], s));
     CU(cudaStreamWaitEvent(sS, m_ready[0], 0));
   }
+  cudaEvent_t ov_ev[2] = {nullptr, nullptr}, ov_none[2] = {nullptr, nullptr};  // fork / join of the pass-1 overlap
+  SyncGuard guard6{ov_ev, ov_none};
+  if (C == 2) {
+    CU(cudaEventCreateWithFlags(&ov_ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ov_ev[1], cudaEventDisableTiming));
+  }
+  cudaEvent_t& ov_fork = ov_ev[0];
+  cudaEvent_t& ov_join = ov_ev[1];
   std::vector<cudaEvent_t> evk;  // timing events on the score stream when it is a separate stream
   EvGuard guard5{evk};
   bool freed_set[2] = {false, false};
@@ -1219,19 +1227,27 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     double* M2b = h->M2[mb].p;
     if (overlap_score && m_free_set[mb]) CU(cudaStreamWaitEvent(s, m_free[mb], 0));  // K3 of batch b-2 has read it
     CU(mark(evs, s));
-    if (C == 2) {
-      const int nWC = B / 128, W = 8;
+    // Pass 1 (issue-slot bound, little shared memory) can run NEXT TO the pass-2 scatter (shared-memory-pipe bound): it is
+    // then launched after the scatter on a second stream, in small blocks that fit into the registers / shared memory the
+    // scatter leaves free on every SM, and joined before K3.
+    const int ov1 = (C == 2) ? env_int("SCDC_OVERLAP_PASS1", 1) : 0;
+    auto launch_pass1 = [&](cudaStream_t sp, int W) -> cudaError_t {
+      const int nWC = B / 128;
       const long long tasks = (long long)h->n_active * nWC;
       const unsigned grid1 = (unsigned)((tasks + W - 1) / W);
       if (env_int("SCDC_U1", 4) == 4)  // 80 registers, 3 blocks / SM; U = 8 (144 registers, 1 block) measured slower
-        scdc::k_pass1_cond<4><<<grid1, W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
-                                                       h->ngroup.p, h->gene_order.p, M1b);
+        scdc::k_pass1_cond<4><<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
+                                                        h->ngroup.p, h->gene_order.p, M1b);
       else
-        scdc::k_pass1_cond<8><<<grid1, W * 32, 0, s>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
-                                                       h->ngroup.p, h->gene_order.p, M1b);
-      CU(cudaGetLastError());
+        scdc::k_pass1_cond<8><<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
+                                                        h->ngroup.p, h->gene_order.p, M1b);
+      return cudaGetLastError();
+    };
+    if (C == 2 && !ov1) {
+      CU(launch_pass1(s, 8));
       ++launches; ++reduce_launches;
     }
+    if (C == 2 && ov1) CU(cudaEventRecord(ov_fork, s));  // labels, means buffers and everything before are ready
     if (early_k2 && done == 0) {
       launches += h->pre.k2_launches;  // batch 0 was reduced behind the matrix upload (upload_matrix_with_early_reduction)
       reduce_launches += h->pre.k2_launches;
@@ -1240,6 +1256,13 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
                        : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, B, M2b, s)
                                      : launch_scatter<1>(h, pl, B, lab2_b, B, M2b, s);
       CU(le);
+      ++launches; ++reduce_launches;
+    }
+    if (C == 2 && ov1) {
+      CU(cudaStreamWaitEvent(h->stream_score, ov_fork, 0));
+      CU(launch_pass1(h->stream_score, env_int("SCDC_W1", 4)));
+      CU(cudaEventRecord(ov_join, h->stream_score));
+      CU(cudaStreamWaitEvent(s, ov_join, 0));
       ++launches; ++reduce_launches;
     }
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
