@@ -986,11 +986,6 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
     CU(cudaStreamWaitEvent(sc, copied, 0));
   }
   bool first = true;
-  const bool dbg = getenv("SCDC_TIMING") != nullptr;
-  std::vector<cudaEvent_t> dbg_ev;
-  std::vector<double> dbg_host;
-  const double dbg_t0 = now_ms();
-  if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sc); dbg_ev.push_back(e); }
   for (int c = 0; c < n_chunks; ++c) {
     const size_t e0 = (size_t)p->colptr[bounds[c]], e1 = (size_t)p->colptr[bounds[c + 1]];
     if (e1 > e0) {
@@ -1015,17 +1010,6 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
                      : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g)
                                    : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g);
     CU(le);
-    if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sk); dbg_ev.push_back(e); dbg_host.push_back(now_ms() - dbg_t0); }
-  }
-  if (dbg) {
-    cudaStreamSynchronize(s); cudaStreamSynchronize(h->stream_labels);
-    for (size_t i = 1; i < dbg_ev.size(); ++i) {
-      float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[0], dbg_ev[i]);
-      fprintf(stderr, "[scdc timing]   chunk %zu: launched at host %.2f ms, K2 done at device %.2f ms\n", i - 1, dbg_host[i - 1], ms);
-    }
-    float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[0], h->pre.t1);
-    fprintf(stderr, "[scdc timing]   labels ready at device %.2f ms\n", ms);
-    for (auto e : dbg_ev) cudaEventDestroy(e);
   }
   if (first) CU(cudaEventRecord(h->pre.k2_t0, s));
   CU(cudaEventRecord(copied, h->stream_labels));  // join the second kernel stream
