@@ -92,6 +92,9 @@ def test_device_philox_labels_match_cpu_restatement(liver_cases, mode, urn, monk
     dict(n_cells=8000, n_genes=30, n_celltypes=60, n_conditions=2, n_lri=40, seed=12, min_group=10),    # NG = 8
     dict(n_cells=6000, n_genes=20, n_celltypes=100, n_conditions=1, n_lri=30, seed=13, min_group=10),   # NG = 16
     dict(n_cells=9000, n_genes=20, n_celltypes=200, n_conditions=1, n_lri=30, seed=14, min_group=10),   # NG = 32
+    dict(n_cells=4003, n_genes=20, n_celltypes=7, n_conditions=2, n_lri=30, seed=15, min_group=10),     # N % 4 != 0
+    dict(n_cells=5001, n_genes=20, n_celltypes=9, n_conditions=1, n_lri=30, seed=16, min_group=10),     # N % 4 != 0
+    dict(n_cells=70001, n_genes=30, n_celltypes=3, n_conditions=2, n_lri=40, seed=17, min_group=10),    # large strata
 ])
 @pytest.mark.parametrize("urn", [0, 1])
 def test_device_philox_labels_match_cpu_restatement_all_urn_widths(kw, urn, monkeypatch):
