@@ -266,7 +266,7 @@ def run_ours(args):
                 "frac": (wavefronts / (ms_reduce / 1e3) / pipe_peak) if ms_reduce > 0 else 0.0,
                 "wavefronts_per_launch": wavefronts / max(1, launches), "sm_mhz": sm_clock,
                 "note": "design wavefronts of the kernel (entry broadcast + fp64 read-modify-write), label loads excluded"
-                        + ("; ncu l1tex__throughput for the same launch is 98.3 %" if args.workload == "config2" else
+                        + ("; ncu l1tex__throughput for the same launch is 98.4 %" if args.workload == "config2" else
                            "; ncu l1tex__throughput: 96 % at K = 50 (config 3), 38-64 % at K = 120 where 7 warps/SM leave "
                            "the kernel latency-bound (profiles/NOTES_r1.md)")}
         traffic = None
@@ -280,7 +280,7 @@ def run_ours(args):
             "bytes_per_launch": bytes_reduce / max(1, launches), "ms_per_launch": ms_reduce / max(1, launches),
             "launches": launches, "binding_unit": pipe,
             "note": "lane = replicate batching makes the kernel shared-memory-pipe bound, not HBM bound (DESIGN.md section 3)"
-                    + (": ncu l1tex__throughput 98.3 % (profiles/r1_final_config2_raw.csv)" if args.workload == "config2" else ""),
+                    + (": ncu l1tex__throughput 98.4 % (profiles/r1m_k_scatter_config2_B10112_raw.csv)" if args.workload == "config2" else ""),
             "unbatched_equivalent_gbs": (12.0 * prob.nnz * prob.n_conditions) * (world * iters * args.steps) / (ms_reduce / 1e3) / 1e9 if ms_reduce > 0 else None,
         }
         shares = {k: sum(s[k] for s in stats_acc) for k in ("ms_labels", "ms_reduce", "ms_score", "ms_device")}
