@@ -139,15 +139,19 @@ class PinnedStager {
     char* buf[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     bool busy = false;
+    int device = -1;  // the events belong to this device: a slot is only reused by copies to the same device
   };
   std::mutex mu_;
   std::vector<Slot*> slots_;
   Slot* acquire() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(mu_);
     for (Slot* sl : slots_)
-      if (!sl->busy) { sl->busy = true; return sl; }
+      if (!sl->busy && sl->device == dev) { sl->busy = true; return sl; }
     Slot* sl = new (std::nothrow) Slot;
     if (!sl) return nullptr;
+    sl->device = dev;
     bool ok = true;
     for (int b = 0; b < 2 && ok; ++b) {
       ok = cudaHostAlloc(reinterpret_cast<void**>(&sl->buf[b]), kChunk, cudaHostAllocPortable) == cudaSuccess &&
