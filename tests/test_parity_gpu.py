@@ -344,3 +344,21 @@ def test_one_shot_detection_call_reduces_batch_0_behind_the_chunked_upload(liver
     n_chunks = min(16, prob.nnz // 5000)
     assert n_chunks >= 8
     assert a["stats"]["reduce_launches"] == n_chunks + 2 and b["stats"]["reduce_launches"] == 3
+
+
+def test_one_shot_differential_call_starts_the_pass2_reduction_before_the_rows_are_installed(liver_cases, monkeypatch):
+    """scdc_perm_counts, differential mode: batch 0's pass-2 scatter is launched right after the matrix upload and the
+    pass-1 copy / rows go up on the copy stream behind it (`launch_early_scatter`). Same counts as the oracle on the
+    CPU restatement of the labels, as the plain path, and as a resident engine."""
+    prob = liver_cases["cond"]["prob"]
+    cond_o, ct_o = oracle_c.philox_labels(prob, 700, seed=37)
+    want, _ = oracle_c.perm_counts(prob, ct_o, cond_o)
+    a = perm_counts(prob, 700, seed=37, batch_size=256)
+    monkeypatch.setenv("SCDC_NO_EARLY_REDUCE", "1")
+    b = perm_counts(prob, 700, seed=37, batch_size=256)
+    monkeypatch.delenv("SCDC_NO_EARLY_REDUCE")
+    with Engine(prob) as eng:
+        c = eng.run(700, seed=37)
+    for got in (a, b, c):
+        assert np.array_equal(got["counts"], want, equal_nan=True)
+    assert a["stats"]["reduce_launches"] == b["stats"]["reduce_launches"] == 2 * 3   # pass 1 + pass 2 per batch of 256
