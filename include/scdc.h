@@ -35,7 +35,8 @@ enum {
   SCDC_ENOGPU = 2, /* no visible CUDA device of compute capability 10.x */
   SCDC_ECUDA = 3,  /* CUDA runtime failure */
   SCDC_ENCCL = 4,  /* NCCL failure (multi-GPU merge of the counters) */
-  SCDC_ENOMEM = 5  /* host or device allocation failure */
+  SCDC_ENOMEM = 5,  /* host or device allocation failure */
+  SCDC_EINTERRUPT = 6 /* scdc_options.interrupt asked to stop; the counters of this call are discarded */
 };
 
 /* score_type (reference argument `score_type`, R/utils_cci.R:605,659) */
@@ -104,6 +105,12 @@ typedef struct scdc_options {
                            first device to use; 0 = default. One process per GPU sets it to its local rank. */
   void* stream;         /* scdc_run only: NULL = the handle's own stream, else a cudaStream_t of the handle's device on
                            which all work of the call is enqueued (lets a caller time it with its own CUDA events) */
+  /* Optional. Polled on the CALLING thread between device batches (never from the library's own threads); a non-zero
+     return abandons the call with SCDC_EINTERRUPT. The .Call wrapper passes a function that runs
+     R_CheckUserInterrupt() under R_ToplevelExec (src/scdc_rcall.c), which is how a long permutation run stays
+     interruptible from the R console, as the reference's future_replicate loop is (R/utils_permutation.R:129-138). */
+  int (*interrupt)(void* user);
+  void* interrupt_user;
 } scdc_options;
 
 typedef struct scdc_stats {

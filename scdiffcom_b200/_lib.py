@@ -11,9 +11,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscdc.so")
 
-SCDC_OK, SCDC_EINVAL, SCDC_ENOGPU, SCDC_ECUDA, SCDC_ENCCL, SCDC_ENOMEM = range(6)
+SCDC_OK, SCDC_EINVAL, SCDC_ENOGPU, SCDC_ECUDA, SCDC_ENCCL, SCDC_ENOMEM, SCDC_EINTERRUPT = range(7)
 SCDC_COUNT_NA = 2**64 - 1
-_ERRNAMES = {1: "SCDC_EINVAL", 2: "SCDC_ENOGPU", 3: "SCDC_ECUDA", 4: "SCDC_ENCCL", 5: "SCDC_ENOMEM"}
+_ERRNAMES = {1: "SCDC_EINVAL", 2: "SCDC_ENOGPU", 3: "SCDC_ECUDA", 4: "SCDC_ENCCL", 5: "SCDC_ENOMEM", 6: "SCDC_EINTERRUPT"}
 
 # every symbol include/scdc.h declares (tests/test_abi.py checks header <-> library <-> this list)
 EXPORTED = (
@@ -44,7 +44,11 @@ class Options(C.Structure):
         ("iterations", C.c_int64), ("seed", C.c_uint64), ("perm_offset", C.c_int64), ("score_type", C.c_int32),
         ("n_gpus", C.c_int32), ("precision", C.c_int32), ("batch_size", C.c_int32), ("perm_cond", C.c_void_p),
         ("perm_ct", C.c_void_p), ("return_distributions", C.c_int32), ("device_base", C.c_int32), ("stream", C.c_void_p),
+        ("interrupt", C.c_void_p), ("interrupt_user", C.c_void_p),
     ]
+
+
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)   # int (*interrupt)(void* user)
 
 
 class Stats(C.Structure):

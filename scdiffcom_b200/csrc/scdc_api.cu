@@ -223,6 +223,7 @@ struct scdc_handle {
   size_t mem_total = 0;
   // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
   std::vector<int> sub_gene_h, gene_nnz_h;
+  const std::atomic<bool>* abort = nullptr;  // multi-GPU: set by the calling thread when the interrupt callback fires
   bool one_shot = false;       // created by scdc_perm_counts for a single run (options known at creation)
   int max_nt = 0, max_nc = 0;  // largest cell type / largest condition (cells): inputs of keygen_plan2
   int n_active = 0;        // genes referenced by the installed rows (gene_order holds them, heaviest first)
@@ -1178,7 +1179,46 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       if (rc) return rc;
     }
   }
-  for (int64_t done = 0; done < o->iterations; done += B) {
+  // Interruptible runs (scdc_options.interrupt, or the abort flag of a multi-GPU call): at most two batches are in flight;
+  // while the host waits for the older one it polls the stop source, and a stop ends the call after the enqueued work.
+  const bool can_stop = o->interrupt != nullptr || h->abort != nullptr;
+  cudaEvent_t batch_ev[2] = {nullptr, nullptr}, batch_none[2] = {nullptr, nullptr};
+  SyncGuard guard7{batch_ev, batch_none};
+  if (can_stop)
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&batch_ev[i], cudaEventDisableTiming));
+  double last_poll = now_ms();
+  auto stop_requested = [&]() -> bool {
+    if (h->abort && h->abort->load(std::memory_order_relaxed)) return true;
+    if (!o->interrupt) return false;
+    const double t = now_ms();
+    if (t - last_poll < 20.0) return false;  // the callback may be expensive (R_ToplevelExec): at most 50 polls / s
+    last_poll = t;
+    return o->interrupt(o->interrupt_user) != 0;
+  };
+  auto wait_polling = [&](cudaEvent_t ev) -> int {  // 0: event reached, 1: stop requested, < 0: CUDA error
+    for (;;) {
+      const cudaError_t q = ev ? cudaEventQuery(ev) : cudaStreamQuery(s);
+      if (q == cudaSuccess) return 0;
+      if (q != cudaErrorNotReady) { fail(SCDC_ECUDA, "cudaEventQuery failed: %s", cudaGetErrorString(q)); return -1; }
+      if (stop_requested()) return 1;
+      std::this_thread::sleep_for(std::chrono::microseconds(500));
+    }
+  };
+  auto interrupted = [&](int64_t done) -> int {
+    cudaStreamSynchronize(s);
+    if (pipelined) cudaStreamSynchronize(sL);
+    cudaStreamSynchronize(h->stream_score);
+    return fail(SCDC_EINTERRUPT, "interrupted by the caller after %lld of %lld replicates were enqueued", (long long)done,
+                (long long)o->iterations);
+  };
+  int64_t batch_no = 0;
+  for (int64_t done = 0; done < o->iterations; done += B, ++batch_no) {
+    if (can_stop && batch_no >= 2) {
+      const int w = wait_polling(batch_ev[batch_no & 1]);  // batch_no - 2 has finished: one batch stays queued behind the running one
+      if (w < 0) return SCDC_ECUDA;
+      if (w > 0) return interrupted(done);
+    }
+    if (can_stop && batch_no > 0 && stop_requested()) return interrupted(done);  // (rate-limited) also when the GPU keeps up
     const int nb = (int)std::min<int64_t>(B, o->iterations - done);
     const int64_t sb_idx = done / SB, in_sb = done % SB;  // position inside the current super-batch
     const int buf = pipelined ? (int)(sb_idx & 1) : 0;
@@ -1332,6 +1372,12 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     }
     CU(mark(evs, s));
     if (uploaded || dist_host) CU(cudaStreamSynchronize(s));  // host source / destination buffers are reused per batch
+    if (can_stop) CU(cudaEventRecord(batch_ev[batch_no & 1], s));
+  }
+  if (can_stop) {
+    const int w = wait_polling(nullptr);
+    if (w < 0) return SCDC_ECUDA;
+    if (w > 0) return interrupted(o->iterations);
   }
   CU(cudaStreamSynchronize(s));
   if (pipelined) CU(cudaStreamSynchronize(sL));
@@ -1523,11 +1569,15 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   std::vector<scdc_stats> sts(W);
   std::vector<scdc_options> os(W, *o);
   const int64_t per = (o->iterations + W - 1) / W;
+  std::atomic<bool> abort_flag{false};
+  std::atomic<int> workers_left{W};
   {
     std::vector<std::thread> th;
     for (int r = 0; r < W; ++r) {
       th.emplace_back([&, r]() {
+        struct Done { std::atomic<int>& n; ~Done() { n.fetch_sub(1); } } done_guard{workers_left};
         memset(&sts[r], 0, sizeof(scdc_stats));
+        os[r].interrupt = nullptr;  // the callback belongs to the calling thread; the workers watch abort_flag
         const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
         os[r].iterations = e - b;
         os[r].perm_offset = o->perm_offset + b;
@@ -1535,6 +1585,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
         if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
         rcs[r] = create_impl(p, ids[r], &hs[r], os[r].iterations > 0 ? &os[r] : nullptr);
         if (rcs[r]) { errs[r] = g_err; return; }
+        if (o->interrupt) hs[r]->abort = &abort_flag;
         if (os[r].iterations > 0) {
           rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
           if (rcs[r]) errs[r] = g_err;
@@ -1544,6 +1595,12 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
           cudaMemset(hs[r]->counts.p, 0, ((size_t)hs[r]->R * hs[r]->ncols + 1) * sizeof(uint32_t));
         }
       });
+    }
+    if (o->interrupt) {
+      while (workers_left.load() > 0) {
+        if (!abort_flag.load() && o->interrupt(o->interrupt_user) != 0) abort_flag.store(true);
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+      }
     }
     for (auto& t : th) t.join();
   }

@@ -87,7 +87,7 @@ class PermutationProblem:
 
 
 def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-             n_cells, keep, device_base=0, stream=None):
+             n_cells, keep, device_base=0, stream=None, interrupt=None):
     o = Options()
     o.iterations = int(iterations)
     o.seed = int(seed) & (2**64 - 1)
@@ -106,6 +106,10 @@ def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm
     o.return_distributions = 1 if return_distributions else 0
     o.device_base = int(device_base)
     o.stream = C.c_void_p(int(stream)) if stream else None
+    if interrupt is not None:   # callable() -> truthy to stop; polled by the library on this thread between batches
+        cb = _lib.INTERRUPT_FN(lambda _user: 1 if interrupt() else 0)
+        keep.append(cb)
+        o.interrupt = C.cast(cb, C.c_void_p)
     return o
 
 
@@ -129,14 +133,14 @@ def version() -> str:
 
 
 def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="geometric_mean", n_gpus=1, perm_offset=0,
-                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0):
+                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0, interrupt=None):
     """One-shot `scdc_perm_counts` with HOST buffers (what the `.Call` wrapper does). Returns dict(counts [R_sub, ncols]
     float64 with NaN = NA, distributions or None, stats)."""
     lib = _lib.load()
     keep = []
     p = problem.c_struct()
     o = _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-                 problem.n_cells, keep, device_base=device_base)
+                 problem.n_cells, keep, device_base=device_base, interrupt=interrupt)
     counts = np.zeros((problem.n_rows, problem.ncols), dtype=np.uint64, order="F")
     res = Result()
     res.counts = _ptr(counts)
@@ -177,11 +181,12 @@ class Engine:
             pass
 
     def run(self, iterations, seed=42, score_type="geometric_mean", perm_offset=0, batch_size=0, perm_cond=None,
-            perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True, stream=None):
+            perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True, stream=None,
+            interrupt=None):
         keep = []
         pr = self.problem
         o = _options(iterations, seed, score_type, perm_offset, 1, batch_size, perm_cond, perm_ct, return_distributions,
-                     pr.n_cells, keep, stream=stream)
+                     pr.n_cells, keep, stream=stream, interrupt=interrupt)
         res = Result()
         counts = None
         if want_host_counts:

@@ -44,6 +44,12 @@ static double opt_num(SEXP opts, const char* name, double dflt) {
  * Returns a double matrix R_sub x ncols of exceedance counts (NA_real_ where the subunit is NA), with attributes
  * "stats" (named numeric) and, when requested, "distributions" (double array R_sub x ncols_d x iterations).
  */
+/* scdc_options.interrupt: R_CheckUserInterrupt() longjmps when the user pressed Ctrl-C / Esc, which must not unwind through
+ * the engine's C++ frames; under R_ToplevelExec the jump is caught and reported as FALSE instead. The engine then stops
+ * enqueuing work, returns SCDC_EINTERRUPT, and the wrapper raises the R-level condition after the call has returned. */
+static void check_interrupt_fn(void* unused) { (void)unused; R_CheckUserInterrupt(); }
+static int poll_user_interrupt(void* unused) { (void)unused; return R_ToplevelExec(check_interrupt_fn, NULL) == FALSE; }
+
 SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SEXP sub_gene, SEXP rows, SEXP observed,
                         SEXP opts) {
   scdc_problem prob;
@@ -86,6 +92,8 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   SEXP pc = list_get(opts, "perm_cond"), pt = list_get(opts, "perm_ct");
   opt.perm_cond = Rf_isNull(pc) ? NULL : RAW(pc);    /* raw matrix N x iterations, column-major == [iterations][N] */
   opt.perm_ct = Rf_isNull(pt) ? NULL : RAW(pt);
+  opt.interrupt = poll_user_interrupt;
+  opt.interrupt_user = NULL;
 
   int nprot = 0;
   const size_t n = (size_t)prob.n_rows * ncols;
@@ -101,6 +109,7 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   const int rc = scdc_perm_counts(&prob, &opt, &res);
   if (rc != SCDC_OK) {
     UNPROTECT(nprot);
+    if (rc == SCDC_EINTERRUPT) Rf_error("scDiffCom B200 backend: interrupted by the user");
     Rf_error("scDiffCom B200 backend: %s (code %d)", scdc_last_error(), rc);
   }
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, prob.n_rows, ncols));

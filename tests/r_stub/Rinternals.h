@@ -41,4 +41,6 @@ void Rf_unprotect(int n);
 #define PROTECT(x) Rf_protect(x)
 #define UNPROTECT(n) Rf_unprotect(n)
 void Rf_error(const char* fmt, ...) __attribute__((noreturn));
+void R_CheckUserInterrupt(void);
+Rboolean R_ToplevelExec(void (*fun)(void* data), void* data);
 #endif

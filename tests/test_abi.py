@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes implied by include/scdc.h on LP64
     assert C.sizeof(_lib.Problem) == 8 * 4 + 10 * 8
-    assert C.sizeof(_lib.Options) == 8 * 3 + 4 * 4 + 2 * 8 + 2 * 4 + 8
+    assert C.sizeof(_lib.Options) == 8 * 3 + 4 * 4 + 2 * 8 + 2 * 4 + 8 + 2 * 8
     assert C.sizeof(_lib.Stats) == 9 * 8 + 3 * 8 + 2 * 4
     assert C.sizeof(_lib.Result) == 3 * 8 + C.sizeof(_lib.Stats)
 

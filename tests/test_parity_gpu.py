@@ -362,3 +362,21 @@ def test_one_shot_differential_call_starts_the_pass2_reduction_before_the_rows_a
     for got in (a, b, c):
         assert np.array_equal(got["counts"], want, equal_nan=True)
     assert a["stats"]["reduce_launches"] == b["stats"]["reduce_launches"] == 2 * 3   # pass 1 + pass 2 per batch of 256
+
+
+def test_interrupt_callback_stops_a_run_and_leaves_the_engine_usable(liver_cases):
+    """scdc_options.interrupt (what the .Call wrapper wires to R_CheckUserInterrupt): polled on the calling thread while
+    at most two batches are in flight; a truthy return ends the call with SCDC_EINTERRUPT. A callback that never fires
+    changes nothing."""
+    prob = liver_cases["cond"]["prob"]
+    polls = []
+    with Engine(prob) as eng:
+        want = eng.run(4096, seed=8, batch_size=128)["counts"]
+        same = eng.run(4096, seed=8, batch_size=128, interrupt=lambda: polls.append(1) and False)["counts"]
+        assert np.array_equal(want, same, equal_nan=True)
+        with pytest.raises(_lib.ScdcError, match="SCDC_EINTERRUPT"):
+            eng.run(200_000, seed=8, batch_size=128, interrupt=lambda: True)
+        again = eng.run(4096, seed=8, batch_size=128)["counts"]
+        assert np.array_equal(want, again, equal_nan=True)
+    with pytest.raises(_lib.ScdcError, match="SCDC_EINTERRUPT"):
+        perm_counts(prob, 200_000, seed=8, batch_size=128, interrupt=lambda: True)
