@@ -256,6 +256,11 @@ def test_in_library_multi_gpu_equals_single_gpu(liver_cases):
         a = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=1)["counts"]
         b = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=2)["counts"]
         assert np.array_equal(a, b, equal_nan=True)
+    # the interrupt callback is polled by the calling thread only; the per-device worker threads watch its flag
+    with pytest.raises(_lib.ScdcError, match="SCDC_EINTERRUPT"):
+        perm_counts(prob, 400_000, seed=3, n_gpus=2, batch_size=128, interrupt=lambda: True)
+    again = perm_counts(prob, 1000, seed=3, n_gpus=2)
+    assert np.array_equal(one["counts"], again["counts"], equal_nan=True)
 
 
 def test_de_column_filter_is_exact():
