@@ -1,5 +1,16 @@
 // scdc_api.cu — host side of the C-ABI declared in include/scdc.h: validation, upload, batch loop, counter merge.
 // The arithmetic lives in scdc_kernels.cuh. No CPU fallback: every compute entry point needs an sm_100 device.
+//
+// Environment knobs (experiments and tests only; the defaults are the measured best):
+//   SCDC_TIMING=1            host phase times on stderr
+//   SCDC_URN_LABELS=1        sequential urn label generator instead of the random-key kernels (also read by the oracle)
+//   SCDC_BMAX, SCDC_SUPER_BATCH   cap of the reduction batch / of the label super-batch (replicates)
+//   SCDC_J, SCDC_W, SCDC_U, SCDC_PAIR   k_scatter: replicates per lane, warps per block, label prefetch depth, pair mode
+//   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1   k_pass1_cond: prefetch depth, warps per block, run next to k_scatter (default 1)
+//   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE   K3 variants
+//   SCDC_NO_EARLY_REDUCE, SCDC_CHUNK_NNZ, SCDC_NO_PRELAUNCH   one-shot call: no reduction behind the upload, chunk size,
+//                            no label pre-launch
+//   SCDC_NO_POOL, SCDC_NO_STAGER   plain cudaMalloc / plain pageable copies
 #include "../../include/scdc.h"
 #include "scdc_kernels.cuh"
 
