@@ -161,6 +161,30 @@ def test_oracle_philox_labels_are_stratified_shuffles(liver_cases):
         assert np.array_equal(ct2, ct[7:12])
 
 
+@pytest.mark.parametrize("urn", ["0", "1"])
+def test_oracle_label_generators_are_uniform_within_strata(liver_cases, urn, monkeypatch):
+    """Both restated generators (random keys, urn) draw every cell's permuted condition with probability
+    n(t, cond2) / n_t inside its cell type, and its permuted cell type from the mixture over the permuted condition
+    (the distribution of base::sample on the reference's strata, R/utils_permutation.R:536-569)."""
+    monkeypatch.setenv("SCDC_URN_LABELS", urn)
+    prob = liver_cases["cond"]["prob"]
+    n = 2000
+    cond, ct = oracle_c.philox_labels(prob, n, seed=11)
+    T, N = prob.n_celltypes, prob.n_cells
+    ct0, cd0 = np.asarray(prob.ct_code), np.asarray(prob.cond_code)
+    base = np.zeros((2, T), np.int64)
+    np.add.at(base, (cd0, ct0), 1)
+    p1 = (base[1] / base.sum(0))[ct0]
+    z = (cond.mean(0) - p1) / np.sqrt(p1 * (1 - p1) / n)
+    assert np.abs(z).max() < 5.5 and abs((z ** 2).sum() - N) < 6 * np.sqrt(2 * N)
+    pc = np.stack([1 - p1, p1], axis=1)
+    pt = pc @ (base / base.sum(1, keepdims=True))
+    obs = np.stack([(ct == t).sum(0) for t in range(T)], axis=1)
+    chi2 = ((obs - n * pt) ** 2 / (n * pt)).sum()
+    dof = N * (T - 1)
+    assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
+
+
 def _naive_counts(prob, pcond, pct, score_type):
     """Third, deliberately naive restatement for tiny problems (pure Python loops, dense means): follows
     run_stat_iteration -> aggregate_cells -> build_cci_or_drate -> counting literally, one replicate at a time."""
