@@ -203,6 +203,25 @@ struct AllocScope {
   ~AllocScope() { g_alloc_stream = prev_s; g_alloc_async = prev_a; }
 };
 
+// Per-device facts and idle stream triplets, kept for the life of the process: a one-shot call then neither queries the
+// driver (cudaMemGetInfo is occasionally slow) nor creates / destroys three streams.
+struct DeviceCache {
+  struct Streams { cudaStream_t s = nullptr, labels = nullptr, score = nullptr; };
+  struct Entry {
+    bool known = false;
+    int num_sms = 0;
+    size_t smem_optin = 0, mem_total = 0;
+    std::vector<Streams> idle;
+  };
+  std::mutex mu;
+  std::vector<Entry> dev;
+  Entry& entry(int d) {
+    if ((int)dev.size() <= d) dev.resize((size_t)d + 1);
+    return dev[(size_t)d];
+  }
+};
+DeviceCache g_devcache;
+
 }  // namespace
 
 struct scdc_handle {
@@ -377,6 +396,7 @@ int scdc_device_count(void) { return count_sm100_devices(nullptr); }
 void scdc_release(scdc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  const int h_device = h->device;
   cudaStream_t s0 = h->stream, s1 = h->stream_labels, s2 = h->stream_score;
   cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1, e2 = h->pre.k2_t0, e3 = h->pre.k2_t1;
   if (s1) cudaStreamSynchronize(s1);  // e.g. labels drawn ahead of a run that never happened
@@ -386,7 +406,19 @@ void scdc_release(scdc_handle* h) {
     if (!s0) g_alloc_async = false;
     delete h;  // buffers go back to the pool in stream order
   }
-  if (s0) { cudaStreamSynchronize(s0); cudaStreamDestroy(s0); }
+  const int device = h_device;
+  if (s0) cudaStreamSynchronize(s0);
+  if (s0 && s1 && s2 && cudaGetLastError() == cudaSuccess) {  // idle and healthy: keep the triplet for the next handle
+    std::lock_guard<std::mutex> lock(g_devcache.mu);
+    DeviceCache::Entry& e = g_devcache.entry(device);
+    if (e.idle.size() < 8) {
+      DeviceCache::Streams st;
+      st.s = s0; st.labels = s1; st.score = s2;
+      e.idle.push_back(st);
+      s0 = s1 = s2 = nullptr;
+    }
+  }
+  if (s0) cudaStreamDestroy(s0);
   if (s1) cudaStreamDestroy(s1);
   if (s2) cudaStreamDestroy(s2);
   if (e0) cudaEventDestroy(e0);
@@ -561,7 +593,16 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
   h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
   h->ncols = (h->C == 2) ? 3 + h->nS : 1;
   h->nnz = (size_t)p->colptr[h->G];
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    std::lock_guard<std::mutex> lock(g_devcache.mu);
+    DeviceCache::Entry& e = g_devcache.entry(device);
+    if (!e.idle.empty()) {
+      h->stream = e.idle.back().s; h->stream_labels = e.idle.back().labels; h->stream_score = e.idle.back().score;
+      e.idle.pop_back();
+    }
+    if (e.known) { h->num_sms = e.num_sms; h->smem_optin = e.smem_optin; h->mem_total = e.mem_total; }
+  }
+  if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   AllocScope alloc_scope(h->stream);
   if (g_alloc_async) {  // keep freed work buffers in the device's default pool for the next call
     cudaMemPool_t pool;
@@ -569,21 +610,24 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     unsigned long long keep = ~0ull;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
-  {  // label generation runs one batch ahead with few, long-lived warps: give its blocks scheduling priority
+  if (!h->stream_labels) {  // label generation runs ahead with few, long-lived warps: give its blocks scheduling priority
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&h->stream_labels, cudaStreamNonBlocking, hi));
     CU(cudaStreamCreateWithPriority(&h->stream_score, cudaStreamNonBlocking, lo));
   }
-  int v = 0;
-  CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
-  h->num_sms = v;
-  CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  h->smem_optin = (size_t)v;
-  {
+  if (h->mem_total == 0) {
+    int v = 0;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    h->num_sms = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    h->smem_optin = (size_t)v;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     h->mem_total = total_b;
+    std::lock_guard<std::mutex> lock(g_devcache.mu);
+    DeviceCache::Entry& e = g_devcache.entry(device);
+    e.known = true; e.num_sms = h->num_sms; e.smem_optin = h->smem_optin; e.mem_total = h->mem_total;
   }
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K;
   cudaStream_t s = h->stream;
