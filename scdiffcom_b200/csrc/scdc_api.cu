@@ -115,12 +115,15 @@ struct DBuf {
 class PinnedStager {
  public:
   static constexpr size_t kChunk = 16u << 20;
-  cudaError_t copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
-    if (bytes < 2 * kChunk || getenv("SCDC_NO_STAGER")) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+  static constexpr int kMaxThreads = 6;
+  // min_bytes: smaller copies go through the driver's own (single-threaded) staging; n_thr: staging threads (<= 6)
+  cudaError_t copy(void* dst, const void* src, size_t bytes, cudaStream_t s, size_t min_bytes = 2 * kChunk,
+                   int n_thr = kMaxThreads) {
+    if (bytes < min_bytes || getenv("SCDC_NO_STAGER")) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
     Slot* slot = acquire();
     if (!slot) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
     cudaError_t rc = cudaSuccess;
-    const int n_thr = 6;
+    n_thr = std::max(1, std::min(n_thr, kMaxThreads));
     size_t off = 0;
     for (int i = 0; off < bytes && rc == cudaSuccess; ++i, off += kChunk) {
       const int b = i & 1;
@@ -129,14 +132,14 @@ class PinnedStager {
       if (rc != cudaSuccess) break;
       char* stage = slot->buf[b];
       const char* from = static_cast<const char*>(src) + off;
-      std::thread th[n_thr - 1];
+      std::thread th[kMaxThreads - 1];
       const size_t part = (n / n_thr + 63) & ~size_t(63);
       for (int t = 1; t < n_thr; ++t) {
         const size_t lo = std::min(n, part * t), hi = std::min(n, part * (t + 1));
         th[t - 1] = std::thread([=]() { if (hi > lo) memcpy(stage + lo, from + lo, hi - lo); });
       }
       memcpy(stage, from, std::min(n, part));
-      for (auto& t : th) t.join();
+      for (int t = 1; t < n_thr; ++t) th[t - 1].join();
       rc = cudaMemcpyAsync(static_cast<char*>(dst) + off, stage, n, cudaMemcpyHostToDevice, s);
       if (rc == cudaSuccess) rc = cudaEventRecord(slot->done[b], s);
     }
@@ -1054,6 +1057,8 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
   for (int c = 0; c < n_chunks; ++c) {
     const size_t e0 = (size_t)p->colptr[bounds[c]], e1 = (size_t)p->colptr[bounds[c + 1]];
     if (e1 > e0) {
+      // (staging the chunks through pinned memory with four host threads, g_stager.copy(.., 1 MB, 4), measured 0.8 ms
+      // slower per call than the driver's own staging of these 3-5 MB pieces on an idle host)
       CU(cudaMemcpyAsync(h->rowidx.p + e0, p->rowidx + e0, (e1 - e0) * sizeof(int), cudaMemcpyHostToDevice, sc));
       CU(cudaMemcpyAsync(h->values.p + e0, p->values + e0, (e1 - e0) * sizeof(double), cudaMemcpyHostToDevice, sc));
     }
