@@ -807,22 +807,24 @@ cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, 
 // sequential urn generator (one thread per replicate); oracle_philox_labels mirrors the same rule.
 cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t perm0, int B, int Bb, int J,
                         uint32_t* bits1, uint8_t* lab2, uint8_t* dbg_cond, uint8_t* dbg_ct) {
-  const int T = h->T;
-  const scdc::KeygenPlan2 kp2 = scdc::keygen_plan2(h->N, T, h->max_nt, h->max_nc);
-  if (h->C == 2 && kp2.ok && !env_int("SCDC_URN_LABELS", 0)) {
-    auto kern = scdc::k_draw_labels_keys2;
+  const int T = h->T, N = h->N;
+  const bool keys_allowed = !env_int("SCDC_URN_LABELS", 0);
+  const scdc::KeygenPlan2 kp2 = scdc::keygen_plan2(N, T, h->max_nt, h->max_nc);
+  const scdc::KeygenPlan kp = scdc::keygen_plan(N, T, h->C);
+  const bool keys2 = keys_allowed && h->C == 2 && kp2.ok, keys1 = keys_allowed && !keys2 && kp.ok;
+  if (keys1 || keys2) {
+    // Random-key generators: one block per replicate writes replicate-major labels (label_tmp, or the caller's debug
+    // arrays), k_relayout_labels transposes them into the reduction's [batch][cell][Bb] blocks (+ condition bit-planes).
+    const bool dbg = dbg_ct || dbg_cond;
     cudaError_t e = cudaSuccess;
-    if (kp2.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp2.smem);
-    if (e != cudaSuccess) return e;
-    if (!h->keyfail.p) {
+    if (!h->keyfail.p) {  // overflow flag of the generators, checked at the end of the run
       e = h->keyfail.alloc(1);
       if (e == cudaSuccess) e = cudaMemsetAsync(h->keyfail.p, 0, sizeof(int), g_alloc_async ? g_alloc_stream : s);
       if (e != cudaSuccess) return e;
     }
-    const bool dbg = dbg_ct || dbg_cond;
     uint8_t* out = nullptr;
     if (!dbg) {
-      e = h->label_tmp.ensure((size_t)h->N * B);
+      e = h->label_tmp.ensure((size_t)N * B);
       if (e != cudaSuccess) return e;
       out = h->label_tmp.p;
     }
@@ -835,49 +837,24 @@ cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t p
       if (e1 != cudaSuccess) return e1;
       if (e2 != cudaSuccess) return e2;
     }
-    kern<<<B, 512, kp2.smem, s>>>(h->N, T, h->ct.p, h->expect.p, seed, perm0, kp2.NB1, kp2.cap1, kp2.NB2, kp2.cap2, out,
-                                  dbg_cond, dbg_ct, h->keyfail.p);
+    if (keys2) {
+      auto kern = scdc::k_draw_labels_keys2;
+      if (kp2.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp2.smem);
+      if (e != cudaSuccess) return e;
+      kern<<<B, 512, kp2.smem, s>>>(N, T, h->ct.p, h->expect.p, seed, perm0, kp2.NB1, kp2.cap1, kp2.NB2, kp2.cap2, out, dbg_cond,
+                                    dbg_ct, h->keyfail.p);
+    } else {
+      auto kern = scdc::k_draw_labels_keys;
+      if (kp.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem);
+      if (e != cudaSuccess) return e;
+      kern<<<B, 256, kp.smem, s>>>(N, T, h->expect.p, seed, perm0, kp.NB, kp.cap, dbg ? dbg_ct : out, h->keyfail.p);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess || dbg) return e;
-    for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks + pass-1 condition bits
-      dim3 grid((h->N + 127) / 128, Bb / 128);
-      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N, T,
-                                                   bits1 + (size_t)b0 / 32 * h->N);
-    }
-    return cudaGetLastError();
-  }
-  const scdc::KeygenPlan kp = scdc::keygen_plan(h->N, T, h->C);
-  if (kp.ok && !env_int("SCDC_URN_LABELS", 0)) {
-    auto kern = scdc::k_draw_labels_keys;
-    cudaError_t e = cudaSuccess;
-    if (kp.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem);
-    if (e != cudaSuccess) return e;
-    if (!h->keyfail.p) {
-      e = h->keyfail.alloc(1);
-      if (e == cudaSuccess) e = cudaMemsetAsync(h->keyfail.p, 0, sizeof(int), g_alloc_async ? g_alloc_stream : s);
-      if (e != cudaSuccess) return e;
-    }
-    uint8_t* out = dbg_ct;
-    if (!out) {
-      e = h->label_tmp.ensure((size_t)h->N * B);
-      if (e != cudaSuccess) return e;
-      out = h->label_tmp.p;
-    }
-    if (s != g_alloc_stream && g_alloc_async) {  // buffers are allocated in the order of the allocation stream
-      cudaEvent_t dep;
-      e = cudaEventCreateWithFlags(&dep, cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
-      cudaError_t e1 = cudaEventRecord(dep, g_alloc_stream), e2 = cudaStreamWaitEvent(s, dep, 0);
-      cudaEventDestroy(dep);
-      if (e1 != cudaSuccess) return e1;
-      if (e2 != cudaSuccess) return e2;
-    }
-    kern<<<B, 256, kp.smem, s>>>(h->N, T, h->expect.p, seed, perm0, kp.NB, kp.cap, out, h->keyfail.p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess || dbg_ct) return e;
-    for (int b0 = 0; b0 < B; b0 += Bb) {  // replicate-major -> [batch][cell][Bb] label blocks of the reduction
-      dim3 grid((h->N + 127) / 128, Bb / 128);
-      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(h->N, Bb, J, out + (size_t)b0 * h->N, lab2 + (size_t)b0 * h->N, 0, nullptr);
+    for (int b0 = 0; b0 < B; b0 += Bb) {
+      dim3 grid((N + 127) / 128, Bb / 128);
+      scdc::k_relayout_labels<<<grid, 256, 0, s>>>(N, Bb, J, out + (size_t)b0 * N, lab2 + (size_t)b0 * N, keys2 ? T : 0,
+                                                   keys2 ? bits1 + (size_t)b0 / 32 * N : nullptr);
     }
     return cudaGetLastError();
   }
