@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCDC_VERSION_STRING "0.1.0"
+#define SCDC_VERSION_STRING "0.2.0"
 
 /* error codes (0 = success) */
 enum {
@@ -42,8 +42,14 @@ enum {
 /* score_type (reference argument `score_type`, R/utils_cci.R:605,659) */
 enum { SCDC_SCORE_GEOMETRIC = 0, SCDC_SCORE_ARITHMETIC = 1 };
 
-/* precision modes. Only SCDC_FP64_EXACT is implemented: fp64 values, the reference's summation order. */
-enum { SCDC_FP64_EXACT = 0 };
+/* precision modes.
+ *   SCDC_FP64_EXACT: fp64 values and sums in the reference's summation order; counts are bit-identical to the reference
+ *                    arithmetic for the same labels.
+ *   SCDC_FP32_FAST : values and group sums in fp32 (same summation order), scores / differences / comparisons in fp64
+ *                    from the fp32 means. Counts may differ from the exact ones only for comparisons that fall inside
+ *                    the tolerance band (scdc_options.rel_tol); every such comparison is reported in
+ *                    scdc_result.band_counts, so |count_fp32 - count_fp64| <= band_count per (row, column). */
+enum { SCDC_FP64_EXACT = 0, SCDC_FP32_FAST = 1 };
 
 /* counts[] entry for a (row, column) whose observed value is NA (absent subunit): the reference yields NA there
  * (R/utils_permutation.R:442-469); the .Call wrapper maps this to NA_real_. */
@@ -67,7 +73,9 @@ enum { SCDC_FP64_EXACT = 0 };
 typedef struct scdc_problem {
   int32_t n_cells;      /* N */
   int32_t n_genes;      /* G */
-  int32_t n_celltypes;  /* T  (<= 127 when n_conditions == 2, <= 255 otherwise) */
+  int32_t n_celltypes;  /* T, with T * n_conditions <= 254 (group codes are 8-bit on the device): T <= 127 in differential
+                           mode, T <= 254 in detection mode; larger inputs are rejected with SCDC_EINVAL and the R glue
+                           keeps the reference's R loop for them */
   int32_t n_conditions; /* C: 1 = detection mode, 2 = differential mode */
   int32_t n_lri;        /* L */
   int32_t n_rows;       /* R_sub */
@@ -92,7 +100,7 @@ typedef struct scdc_options {
                            partition of [0, total) over calls / GPUs / processes reproduces the same labels */
   int32_t score_type;   /* SCDC_SCORE_* */
   int32_t n_gpus;       /* scdc_perm_counts only: 0 = all visible devices, k = first k devices */
-  int32_t precision;    /* SCDC_FP64_EXACT */
+  int32_t precision;    /* SCDC_FP64_EXACT (default) or SCDC_FP32_FAST */
   int32_t batch_size;   /* replicates per device launch; 0 = auto */
   /* validation mode: the reference's own permuted labels, row-major [iterations][N] (replicate-major).
      detection: perm_ct = sample(cell_type) codes (R/utils_permutation.R:509); perm_cond must be NULL.
@@ -111,6 +119,12 @@ typedef struct scdc_options {
      interruptible from the R console, as the reference's future_replicate loop is (R/utils_permutation.R:129-138). */
   int (*interrupt)(void* user);
   void* interrupt_user;
+  /* SCDC_FP32_FAST only: relative half-width of the tie band (<= 0: the default 1e-5). A comparison `perm >= obs` is
+     "in the band" when |perm - obs| <= rel_tol * scale, scale = |obs| for the one-sided score columns (geometric scores
+     are compared as products: |x - obs^2| <= 2 rel_tol obs^2) and = the sum of the two magnitudes being subtracted for
+     the two-sided difference columns (DE: score_cond2 + score_cond1; subunits: mean_cond2 + mean_cond1), which is the
+     scale of the fp32 rounding error of a difference. */
+  double rel_tol;
 } scdc_options;
 
 typedef struct scdc_stats {
@@ -128,7 +142,10 @@ typedef struct scdc_stats {
   int64_t kernel_launches; /* all kernels launched by the call */
   int64_t batch_size;   /* replicates per launch actually used */
   int32_t n_gpus;       /* devices actually used */
-  int32_t reserved;
+  int32_t reserved;     /* multi-GPU calls: 1 = NCCL did the broadcast / merge, 0 = peer copies (NCCL unavailable) */
+  double h2d_bytes;     /* bytes copied host -> device by the call (problem, rows, uploaded labels) */
+  double d2h_bytes;     /* bytes copied device -> host (counters, distributions) */
+  double p2p_bytes;     /* bytes copied device -> device over NVLink (multi-GPU: the problem is uploaded once and broadcast) */
 } scdc_stats;
 
 typedef struct scdc_result {
@@ -137,6 +154,10 @@ typedef struct scdc_result {
                              column-major R_sub x ncols_d matrix); ncols_d = 1 (detection) or 3 (DE, cond1, cond2) */
   void* counts_device;    /* scdc_run only: NULL, or a DEVICE buffer of int64[R_sub * ncols] on the handle's device
                              that receives the raw counts (NA entries = 0) for a caller-side collective */
+  uint64_t* band_counts;  /* NULL, or caller-allocated [R_sub * ncols] column-major: comparisons inside the tolerance band
+                             (SCDC_FP32_FAST; all zero in SCDC_FP64_EXACT, where nothing is approximated). NA entries as
+                             in counts */
+  void* band_device;      /* scdc_run only: like counts_device, for the band counters */
   scdc_stats stats;
 } scdc_result;
 
@@ -179,6 +200,29 @@ typedef struct scdc_observed {
 int scdc_observed_pass(scdc_handle* handle, int64_t n, const int32_t* row_lri, const int32_t* row_emit,
                        const int32_t* row_recv, double threshold_pct, double threshold_min_cells, int32_t score_type,
                        scdc_observed* out);
+
+/* ---- "next" item f3: the CJ template and the merge-back, integer-coded, from the shim --------------
+ * Host-side helpers (no device needed): at T = 60 the reference builds these with CJ() + string-keyed merges over 18 M rows
+ * (R/utils_cci.R:1-169) and merges the p-values back with another keyed merge (R/utils_permutation.R:427-469); here they are
+ * O(rows) integer loops over a few host threads, and R attaches the factor levels once.
+ *
+ * scdc_cci_template = create_cci_template + add_cell_number (R/utils_cci.R:1-30, 89-169). Row i of the template
+ * (CJ order: emitter, receiver, LRI name ascending) is emitter = i / (T * L), receiver = (i / L) % T, LRI = lri_order[i % L],
+ * where lri_order[L] lists the LRI indices sorted by name (order(LRI$LRI) - 1L; CJ sorts its arguments). Outputs, each
+ * caller-allocated with n = T * T * L entries (ncells_*: [C][n], condition-major): emitter / receiver cell-type codes, LRI
+ * index, and NCELLS_EMITTER / NCELLS_RECEIVER (per condition in differential mode). Any output may be NULL. */
+int scdc_cci_template(int32_t n_celltypes, int32_t n_conditions, int32_t n_lri, const int32_t* lri_order, int32_t n_cells,
+                      const int32_t* ct_code, const int32_t* cond_code, int32_t* emitter, int32_t* receiver,
+                      int32_t* lri_idx, int32_t* ncells_emitter, int32_t* ncells_receiver);
+
+/* scdc_merge_pvalues = R/utils_permutation.R:215-259 (p = counts / iterations) + :427-469 (merge back into the full table):
+ * pvalues is caller-allocated, column-major [n_full x ncols]; rows outside the tested subset get 1 in every column
+ * (:434-441); tested row k (position tested_rows[k] of the full table) gets counts[k] / iterations, NaN for SCDC_COUNT_NA;
+ * and in differential mode (ncols = 3 + max_nL + max_nR) the subunit columns are NaN (= NA) wherever the row's LRI lacks
+ * that subunit (:442-469), tested or not. lri_idx[n_full] = LRI index of every full row; sub_gene as in scdc_problem. */
+int scdc_merge_pvalues(int64_t n_full, int64_t n_tested, const int64_t* tested_rows, int32_t ncols, const uint64_t* counts,
+                       int64_t iterations, int32_t n_lri, int32_t max_nL, int32_t max_nR, const int32_t* sub_gene,
+                       const int32_t* lri_idx, double* pvalues);
 
 /* Debug / test hook: the labels scdc_run would draw on the device for replicates [perm_offset, perm_offset + n),
  * row-major [n][N]. cond_out may be NULL in detection mode. */

@@ -38,10 +38,11 @@ def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
 
 
-def perm_counts(problem, perm_ct, perm_cond=None, score_type=0, return_distributions=False, nthreads=0):
+def perm_counts(problem, perm_ct, perm_cond=None, score_type=0, return_distributions=False, nthreads=0, de_scale=None):
     """problem: any object with the scdc_problem fields (e.g. scdiffcom_b200.PermutationProblem).
     perm_ct / perm_cond: uint8 [iterations, N]. Returns (counts float64 [R, ncols] with NaN where observed is NaN,
-    distributions [iterations, ncols_d, R] or None)."""
+    distributions [iterations, ncols_d, R] or None). de_scale: optional float64 [iterations, R] output (differential mode):
+    pass-1 score of cond2 + of cond1, the scale of the DE column's rounding error."""
     lib = load()
     N, G, T, Cn = problem.n_cells, problem.n_genes, problem.n_celltypes, problem.n_conditions
     nL, nR = problem.max_nL, problem.max_nR
@@ -61,10 +62,11 @@ def perm_counts(problem, perm_ct, perm_cond=None, score_type=0, return_distribut
     values = np.ascontiguousarray(problem.values, dtype=np.float64)
     ct, rl, re_, rr = _i32(problem.ct_code), _i32(problem.row_lri), _i32(problem.row_emit), _i32(problem.row_recv)
     lib.oracle_perm_counts.argtypes = [C.c_int] * 8 + [C.c_void_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
-                                                                          C.c_void_p, C.c_void_p, C.c_int]
+                                                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     rc = lib.oracle_perm_counts(N, G, T, Cn, sub_gene.shape[0], R, nL, nR, _p(colptr), _p(rowidx), _p(values), _p(ct),
                                 _p(sub_gene), _p(rl), _p(re_), _p(rr), _p(obs), iters,
-                                int(score_type), _p(perm_cond), _p(perm_ct), _p(counts), _p(dist), int(nthreads))
+                                int(score_type), _p(perm_cond), _p(perm_ct), _p(counts), _p(dist), int(nthreads),
+                                _p(de_scale))
     if rc:
         raise MemoryError("oracle_perm_counts: allocation failed")
     out = counts.astype(np.float64)

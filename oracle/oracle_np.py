@@ -238,14 +238,22 @@ def run_simple_cci_analysis(ai, tmpl, score_type="geometric_mean", threshold_min
     names_d, dr = aggregate_cells(X, ai["metadata"], cond["is_cond"])
     out = build_cci_or_drate(names_d, dr, ai["genes"], cci, ai["max_nL"], ai["max_nR"], cond, "drate", score_type,
                              threshold_min_cells=threshold_min_cells, threshold_pct=threshold_pct)
-    if cond["is_cond"]:                                                # :284-437 (non-log scale branch)
+    if cond["is_cond"]:                                                # :284-437
         c1, c2 = cond["cond1"], cond["cond2"]
+        sub = [f"L{i}" for i in range(1, ai["max_nL"] + 1)] + [f"R{j}" for j in range(1, ai["max_nR"] + 1)]
+        gene_cols = [f"LIGAND_{i}" for i in range(1, ai["max_nL"] + 1)] + [f"RECEPTOR_{j}" for j in range(1, ai["max_nR"] + 1)]
         with np.errstate(divide="ignore", invalid="ignore"):
-            if log_scale:
+            if log_scale:                                              # :299-352: plain differences, nothing replaced
                 lfc = out[f"CCI_SCORE_{c2}"] - out[f"CCI_SCORE_{c1}"]
-            else:
+                for name in sub:
+                    out[f"{name}_LOGFC"] = out[f"{name}_EXPRESSION_{c2}"] - out[f"{name}_EXPRESSION_{c1}"]
+            else:                                                      # :353-433: log of the ratio, NaN (0/0) -> 0;
                 lfc = np.log(out[f"CCI_SCORE_{c2}"] / out[f"CCI_SCORE_{c1}"])
                 lfc = np.where(np.isnan(lfc), 0.0, lfc)
+                for name, gcol in zip(sub, gene_cols):
+                    t = np.log(out[f"{name}_EXPRESSION_{c2}"] / out[f"{name}_EXPRESSION_{c1}"])
+                    absent = np.array([x == NA for x in tmpl[gcol].tolist()])   # NA subunit: is.nan(NA) is FALSE, NA is kept
+                    out[f"{name}_LOGFC"] = np.where(absent, np.nan, np.where(np.isnan(t), 0.0, t))
         out["LOGFC"] = lfc
         out["LOGFC_ABS"] = np.abs(lfc)
     return out

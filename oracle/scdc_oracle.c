@@ -73,13 +73,15 @@ static double row_score(const oracle_problem* p, const double* means, int cond, 
 /*
  * perm_cond / perm_ct: replicate-major [iterations][N] label codes (perm_cond NULL in detection mode).
  * counts: column-major [R][ncols] uint64 (zeroed here). dist: NULL or [iterations][ncols_d][R].
+ * de_scale: NULL or [iterations][R] (differential mode): pass-1 score of cond2 + pass-1 score of cond1, the magnitude a
+ * rounding error of the DE column scales with (used by the tests of the fp32-fast mode).
  * nthreads <= 0: all OpenMP threads.
  */
 int oracle_perm_counts(int N, int G, int T, int C, int L, int R, int nL, int nR, const int32_t* colptr,
                        const int32_t* rowidx, const double* values, const int32_t* ct_code, const int32_t* sub_gene,
                        const int32_t* row_lri, const int32_t* row_emit, const int32_t* row_recv, const double* observed,
                        int64_t iterations, int score_type, const uint8_t* perm_cond, const uint8_t* perm_ct,
-                       uint64_t* counts, double* dist, int nthreads) {
+                       uint64_t* counts, double* dist, int nthreads, double* de_scale) {
   oracle_problem P = {N, G, T, C, L, R, nL, nR, colptr, rowidx, values, sub_gene, row_lri, row_emit, row_recv, observed};
   const int K = C * T, nS = nL + nR, ncols = (C == 2) ? 3 + nS : 1, ncols_d = (C == 2) ? 3 : 1;
   memset(counts, 0, sizeof(uint64_t) * (size_t)R * ncols);
@@ -133,6 +135,7 @@ int oracle_perm_counts(int N, int G, int T, int C, int L, int R, int nL, int nR,
               double* d = dist + ((size_t)it * ncols_d) * R + r;
               d[0] = de; d[(size_t)R] = s2c1; d[(size_t)2 * R] = s2c2;
             }
+            if (de_scale) de_scale[(size_t)it * R + r] = s1c2 + s1c1;
           }
         }
       }

@@ -13,12 +13,14 @@ LIB_PATH = os.path.join(_HERE, "libscdc.so")
 
 SCDC_OK, SCDC_EINVAL, SCDC_ENOGPU, SCDC_ECUDA, SCDC_ENCCL, SCDC_ENOMEM, SCDC_EINTERRUPT = range(7)
 SCDC_COUNT_NA = 2**64 - 1
+PRECISIONS = {"fp64": 0, "fp64_exact": 0, "fp32_fast": 1}
+HAS_FP32_FAST = True   # SCDC_FP32_FAST is implemented by this library version (bench.py reports it under an extra key)
 _ERRNAMES = {1: "SCDC_EINVAL", 2: "SCDC_ENOGPU", 3: "SCDC_ECUDA", 4: "SCDC_ENCCL", 5: "SCDC_ENOMEM", 6: "SCDC_EINTERRUPT"}
 
 # every symbol include/scdc.h declares (tests/test_abi.py checks header <-> library <-> this list)
 EXPORTED = (
     "scdc_perm_counts", "scdc_create", "scdc_run", "scdc_release", "scdc_group_means", "scdc_draw_labels",
-    "scdc_set_rows", "scdc_observed_pass", "scdc_trim",
+    "scdc_set_rows", "scdc_observed_pass", "scdc_trim", "scdc_cci_template", "scdc_merge_pvalues",
     "scdc_selftest_de_filter", "scdc_last_error", "scdc_device_count", "scdc_version",
 )
 
@@ -44,7 +46,7 @@ class Options(C.Structure):
         ("iterations", C.c_int64), ("seed", C.c_uint64), ("perm_offset", C.c_int64), ("score_type", C.c_int32),
         ("n_gpus", C.c_int32), ("precision", C.c_int32), ("batch_size", C.c_int32), ("perm_cond", C.c_void_p),
         ("perm_ct", C.c_void_p), ("return_distributions", C.c_int32), ("device_base", C.c_int32), ("stream", C.c_void_p),
-        ("interrupt", C.c_void_p), ("interrupt_user", C.c_void_p),
+        ("interrupt", C.c_void_p), ("interrupt_user", C.c_void_p), ("rel_tol", C.c_double),
     ]
 
 
@@ -58,14 +60,18 @@ class Stats(C.Structure):
         ("reduce_wavefronts", C.c_double),
         ("reduce_launches", C.c_int64), ("kernel_launches", C.c_int64), ("batch_size", C.c_int64),
         ("n_gpus", C.c_int32), ("reserved", C.c_int32),
+        ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("p2p_bytes", C.c_double),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        d = {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        d["used_nccl"] = int(self.reserved)   # multi-GPU calls: 1 = NCCL broadcast / all-reduce, 0 = peer copies
+        return d
 
 
 class Result(C.Structure):
-    _fields_ = [("counts", C.c_void_p), ("distributions", C.c_void_p), ("counts_device", C.c_void_p), ("stats", Stats)]
+    _fields_ = [("counts", C.c_void_p), ("distributions", C.c_void_p), ("counts_device", C.c_void_p),
+                ("band_counts", C.c_void_p), ("band_device", C.c_void_p), ("stats", Stats)]
 
 
 class Observed(C.Structure):
@@ -100,6 +106,9 @@ def load():
     lib.scdc_observed_pass.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                        C.c_int32, C.POINTER(Observed)]
     lib.scdc_trim.argtypes = [C.c_int32]
+    lib.scdc_cci_template.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 7
+    lib.scdc_merge_pvalues.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scdc_selftest_de_filter.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

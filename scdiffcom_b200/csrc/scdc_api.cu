@@ -81,6 +81,8 @@ int env_int(const char* name, int dflt) {
 // "allocation stream" (the handle's stream, set by every API entry point); other streams are made to wait on it.
 thread_local cudaStream_t g_alloc_stream = nullptr;
 thread_local bool g_alloc_async = false;
+// bytes this thread has asked the driver to copy (scdc_stats.h2d_bytes / d2h_bytes / p2p_bytes)
+thread_local double g_h2d_bytes = 0, g_d2h_bytes = 0, g_p2p_bytes = 0;
 
 template <typename T>
 struct DBuf {
@@ -104,6 +106,7 @@ struct DBuf {
   cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
     cudaError_t e = alloc(count);
     if (e != cudaSuccess || count == 0) return e;
+    g_h2d_bytes += (double)(count * sizeof(T));
     return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
   }
 };
@@ -124,25 +127,47 @@ class PinnedStager {
     if (!slot) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
     cudaError_t rc = cudaSuccess;
     n_thr = std::max(1, std::min(n_thr, kMaxThreads));
-    size_t off = 0;
-    for (int i = 0; off < bytes && rc == cudaSuccess; ++i, off += kChunk) {
-      const int b = i & 1;
-      const size_t n = std::min(kChunk, bytes - off);
+    const long n_chunks = (long)((bytes + kChunk - 1) / kChunk);
+    // The helper threads live for the whole copy (not per chunk): chunk i may be filled once open_chunk >= i, i.e. once the
+    // DMA that last read its staging buffer has finished; filled[b] counts the helpers that are done with buffer b.
+    std::atomic<long> open_chunk{-1};
+    std::atomic<int> filled[2];
+    filled[0].store(0); filled[1].store(0);
+    auto slice = [&](long i, int t) {
+      const size_t off = (size_t)i * kChunk, n = std::min(kChunk, bytes - off);
+      const size_t part = (n / n_thr + 63) & ~size_t(63);
+      const size_t lo = std::min(n, part * t), hi = std::min(n, part * (t + 1));
+      if (hi > lo) memcpy(slot->buf[i & 1] + lo, static_cast<const char*>(src) + off + lo, hi - lo);
+    };
+    std::vector<std::thread> helpers;
+    try {
+      for (int t = 1; t < n_thr; ++t)
+        helpers.emplace_back([&, t]() {
+          for (long i = 0; i < n_chunks; ++i) {
+            while (open_chunk.load(std::memory_order_acquire) < i) std::this_thread::yield();
+            if (open_chunk.load(std::memory_order_acquire) >= n_chunks) return;  // the copy was abandoned
+            slice(i, t);
+            filled[i & 1].fetch_add(1, std::memory_order_release);
+          }
+        });
+    } catch (...) {  // fewer threads than planned: the slices are cut for n_thr, so the calling thread covers the missing ones
+    }
+    const int n_help = (int)helpers.size();
+    for (long i = 0; i < n_chunks && rc == cudaSuccess; ++i) {
+      const int b = (int)(i & 1);
+      const size_t off = (size_t)i * kChunk, n = std::min(kChunk, bytes - off);
       if (i >= 2) rc = cudaEventSynchronize(slot->done[b]);  // the DMA that last read this staging buffer has finished
       if (rc != cudaSuccess) break;
-      char* stage = slot->buf[b];
-      const char* from = static_cast<const char*>(src) + off;
-      std::thread th[kMaxThreads - 1];
-      const size_t part = (n / n_thr + 63) & ~size_t(63);
-      for (int t = 1; t < n_thr; ++t) {
-        const size_t lo = std::min(n, part * t), hi = std::min(n, part * (t + 1));
-        th[t - 1] = std::thread([=]() { if (hi > lo) memcpy(stage + lo, from + lo, hi - lo); });
-      }
-      memcpy(stage, from, std::min(n, part));
-      for (int t = 1; t < n_thr; ++t) th[t - 1].join();
-      rc = cudaMemcpyAsync(static_cast<char*>(dst) + off, stage, n, cudaMemcpyHostToDevice, s);
+      filled[b].store(0, std::memory_order_relaxed);
+      open_chunk.store(i, std::memory_order_release);
+      slice(i, 0);
+      for (int t = n_help + 1; t < n_thr; ++t) slice(i, t);
+      while (filled[b].load(std::memory_order_acquire) < n_help) std::this_thread::yield();
+      rc = cudaMemcpyAsync(static_cast<char*>(dst) + off, slot->buf[b], n, cudaMemcpyHostToDevice, s);
       if (rc == cudaSuccess) rc = cudaEventRecord(slot->done[b], s);
     }
+    open_chunk.store(n_chunks, std::memory_order_release);  // releases helpers that are still waiting (error path)
+    for (auto& t : helpers) t.join();
     if (rc == cudaSuccess) { cudaEventSynchronize(slot->done[0]); cudaEventSynchronize(slot->done[1]); }
     release(slot);
     return rc;
@@ -192,6 +217,7 @@ template <typename T>
 cudaError_t upload_big(DBuf<T>& buf, const T* src, size_t count, cudaStream_t s) {
   cudaError_t e = buf.alloc(count);
   if (e != cudaSuccess || count == 0) return e;
+  g_h2d_bytes += (double)(count * sizeof(T));
   return g_stager.copy(buf.p, src, count * sizeof(T), s);
 }
 
@@ -235,24 +261,27 @@ struct scdc_handle {
   int num_sms = 148;
   size_t smem_optin = 0;
   // problem
-  DBuf<int> colptr, rowidx, segptr, rowidx_s, gene_order, sub_gene, row_lri, row_emit, row_recv;
-  DBuf<double> values, values_s, ngroup, obs;
+  DBuf<int> colptr, rowidx, segptr, gene_order, sub_gene, row_lri, row_emit, row_recv;
+  DBuf<double> values, ngroup, obs;
+  DBuf<uint4> rec_s;      // pass-1 copy of the matrix: (cell, value) records, inside each gene column sorted by cell type
+  DBuf<float> values_f;   // SCDC_FP32_FAST: fp32 copies of the values / of the pass-1 records (made on the device at the
+  DBuf<uint2> rec_sf;     //                 first fp32 run)
   DBuf<uint8_t> ct, cond;
   DBuf<uint32_t> expect;      // n(cell type, condition) as uint32 [K]
   DBuf<int> visit, ct_seg;     // K1 visit order (differential: cells stably sorted by cell type) and its segments
-  std::vector<uint8_t> obs_na;  // host: 1 where observed is NaN
+  std::shared_ptr<std::vector<uint8_t>> obs_na;  // host: 1 where observed is NaN (shared by the clones of a multi-GPU call)
   // K3: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
   DBuf<double> thr, obs_sub;   // obs_sub: [L][T][nS] common observed subunit differences (factorised subunit columns)
   bool fact_ok = false;
   int n_tasks = 0, score_threads = 256;
   // per-run workspace (grown on demand)
-  DBuf<uint32_t> bits1[2], counts;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
+  DBuf<uint32_t> bits1[2], counts, band;   // label buffers are double-buffered (K1 runs one batch ahead on stream_labels)
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
   DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
   DBuf<int> flag, early_genes, keyfail;   // keyfail: overflow flag of the random-key label generator
   DBuf<uint8_t> label_tmp;               // replicate-major labels of the random-key generator before re-layout
-  double ms_upload = 0;
+  double ms_upload = 0, h2d_bytes = 0;   // scdc_create: wall time and bytes copied host -> device
   size_t mem_total = 0;
   // host copies needed to (re)install tested rows: sub_gene table and per-gene nnz
   std::vector<int> sub_gene_h, gene_nnz_h;
@@ -303,9 +332,9 @@ int count_sm100_devices(std::vector<int>* ids) {
 
 // O(nnz) part of the validation: cell indices in range and strictly ascending inside every gene column.
 // progress (optional) = number of leading gene columns already found valid.
-int validate_matrix(const scdc_problem* p, std::atomic<int>* progress = nullptr) {
-  const int N = p->n_cells, G = p->n_genes;
-  for (int g = 0; g < G; ++g) {
+int validate_matrix_range(const scdc_problem* p, int g_lo, int g_hi, std::atomic<int>* progress) {
+  const int N = p->n_cells;
+  for (int g = g_lo; g < g_hi; ++g) {
     if (progress && (g & 15) == 0) progress->store(g, std::memory_order_release);
     for (int e = p->colptr[g]; e < p->colptr[g + 1]; ++e) {
       int c = p->rowidx[e];
@@ -314,7 +343,39 @@ int validate_matrix(const scdc_problem* p, std::atomic<int>* progress = nullptr)
         return fail(SCDC_EINVAL, "rowidx not strictly ascending inside gene column %d", g);
     }
   }
-  if (progress) progress->store(G, std::memory_order_release);
+  if (progress) progress->store(g_hi, std::memory_order_release);
+  return SCDC_OK;
+}
+
+// n_thr > 1 (and no progress counter): gene ranges of about equal nnz are checked by n_thr host threads; the failure in the
+// lowest gene range is the one reported, as the sequential scan would.
+int validate_matrix(const scdc_problem* p, std::atomic<int>* progress = nullptr, int n_thr = 1) {
+  const int G = p->n_genes;
+  const long long nnz = p->colptr[G];
+  if (progress || n_thr <= 1 || nnz < (1 << 22)) return validate_matrix_range(p, 0, G, progress);
+  std::vector<int> bounds(1, 0);
+  for (int w = 1; w <= n_thr; ++w) {
+    const long long target = nnz * w / n_thr;
+    int g = bounds.back();
+    while (g < G && (w == n_thr || p->colptr[g + 1] <= target)) ++g;
+    bounds.push_back(g);
+  }
+  std::vector<int> rcs((size_t)n_thr, SCDC_OK);
+  std::vector<std::string> errs((size_t)n_thr);
+  std::vector<std::thread> th;
+  auto body = [&](int w) {
+    rcs[w] = validate_matrix_range(p, bounds[w], bounds[w + 1], nullptr);
+    if (rcs[w]) errs[w] = g_err;
+  };
+  try {
+    for (int w = 1; w < n_thr; ++w) th.emplace_back(body, w);
+  } catch (...) {  // no more threads: the calling thread checks the ranges that got none
+    for (int w = (int)th.size() + 1; w < n_thr; ++w) body(w);
+  }
+  body(0);
+  for (auto& t : th) t.join();
+  for (int w = 0; w < n_thr; ++w)
+    if (rcs[w]) { g_err = errs[w]; return rcs[w]; }
   return SCDC_OK;
 }
 
@@ -369,7 +430,7 @@ int validate_meta(const scdc_problem* p) {
 
 int validate_problem(const scdc_problem* p) {
   int rc = validate_meta(p);
-  return rc ? rc : validate_matrix(p);
+  return rc ? rc : validate_matrix(p, nullptr, 4);
 }
 
 int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* o) {
@@ -379,7 +440,9 @@ int validate_options(const scdc_problem* /*unused*/, int C, const scdc_options* 
   if (o->perm_offset < 0) return fail(SCDC_EINVAL, "perm_offset must be >= 0");
   if (o->score_type != SCDC_SCORE_GEOMETRIC && o->score_type != SCDC_SCORE_ARITHMETIC)
     return fail(SCDC_EINVAL, "unknown score_type %d", o->score_type);
-  if (o->precision != SCDC_FP64_EXACT) return fail(SCDC_EINVAL, "only precision = SCDC_FP64_EXACT is implemented");
+  if (o->precision != SCDC_FP64_EXACT && o->precision != SCDC_FP32_FAST)
+    return fail(SCDC_EINVAL, "precision must be SCDC_FP64_EXACT or SCDC_FP32_FAST");
+  if (std::isnan(o->rel_tol) || o->rel_tol > 0.5) return fail(SCDC_EINVAL, "rel_tol must be a number <= 0.5 (<= 0: the default 1e-5)");
   if (o->batch_size < 0) return fail(SCDC_EINVAL, "batch_size must be >= 0");
   if (C == 1 && o->perm_cond) return fail(SCDC_EINVAL, "perm_cond given in detection mode");
   if (C == 2 && ((o->perm_cond != nullptr) != (o->perm_ct != nullptr)))
@@ -473,7 +536,8 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   CU(h->row_emit.upload(row_emit, n_rows, s));
   CU(h->row_recv.upload(row_recv, n_rows, s));
   CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
-  h->obs_na.resize((size_t)n_rows * h->ncols);
+  h->obs_na = std::make_shared<std::vector<uint8_t>>((size_t)n_rows * h->ncols);
+  std::vector<uint8_t>& obs_na = *h->obs_na;
   const int n_thr = ((size_t)n_rows * h->ncols > (1u << 20)) ? 4 : 1;  // a few host threads on large tables
   auto parallel = [&](auto&& fn) {
     std::vector<std::thread> th;
@@ -482,8 +546,8 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
     for (auto& t : th) t.join();
   };
   parallel([&](int w) {
-    const size_t n = h->obs_na.size(), lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
-    for (size_t i = lo; i < hi; ++i) h->obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
+    const size_t n = obs_na.size(), lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
+    for (size_t i = lo; i < hi; ++i) obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
   });
   // K3 work list: rows stably sorted by LRI (counting sort), each LRI cut into slices of score_threads * kScoreRPT rows
   std::vector<int> srow(n_rows), t_lri, t_beg, t_end;
@@ -516,7 +580,7 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   }
   std::vector<double> obs_sub;
   h->fact_ok = false;
-  if (C == 2 && (long long)T * h->nS <= 2 * kScoreThreads) {
+  if (C == 2) {
     // The subunit columns of a row depend only on (LRI, emitter) / (LRI, receiver). If the observed subunit
     // differences agree bitwise across the rows sharing such a pair (true for tables built by the reference, where they
     // are joins of the same group means), K3 counts them once per (cell type, subunit).
@@ -556,46 +620,22 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   return SCDC_OK;
 }
 
-// o_hint != NULL (one-shot path): the options of the run that follows. The cheap part of the validation has been done by
-// the caller; the O(nnz) matrix check runs on a helper thread and K1 is launched ahead, both overlapping the H2D copies.
-static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, const scdc_options* o_hint) {
-  if (!out) return fail(SCDC_EINVAL, "out is NULL");
-  *out = nullptr;
-  PhaseTimer pt;
-  int rc = o_hint ? SCDC_OK : validate_problem(p);
-  if (rc) return rc;
-  pt.lap("create: validate");
-  int matrix_rc = SCDC_OK;
-  std::string matrix_err;
-  std::thread matrix_check;
-  struct Joiner {
-    std::thread& t;
-    ~Joiner() { if (t.joinable()) t.join(); }
-  } joiner{matrix_check};
-  std::atomic<int> genes_valid{0};
-  std::atomic<bool> matrix_done{false};
-  if (o_hint)
-    matrix_check = std::thread([&]() {
-      matrix_rc = validate_matrix(p, &genes_valid);
-      if (matrix_rc) matrix_err = g_err;
-      matrix_done.store(true, std::memory_order_release);
-    });
-  std::vector<int> ids;
-  if (count_sm100_devices(&ids) == 0)
-    return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
-  if (device < 0) device = ids[0];
-  if (std::find(ids.begin(), ids.end(), (int)device) == ids.end())
-    return fail(SCDC_ENOGPU, "device %d is not a visible compute-capability-10.x device", device);
-  const double t0 = now_ms();
+// segptr / rec_s from colptr / rowidx / values / ct, all on the device (k_sort_by_celltype), enqueued on `s`
+static int build_pass1_copy(scdc_handle* h, cudaStream_t s) {
+  const int G = h->G, T = h->T;
+  CU(h->segptr.alloc((size_t)G * (T + 1)));
+  CU(h->rec_s.alloc(h->nnz ? h->nnz : 1));
+  const int W = 8;
+  scdc::k_sort_by_celltype<<<(G + W - 1) / W, W * 32, (size_t)W * (T + 1) * sizeof(int), s>>>(
+      G, T, h->colptr.p, h->rowidx.p, h->values.p, h->ct.p, nullptr, h->segptr.p, h->rec_s.p);
+  CU(cudaGetLastError());
+  return SCDC_OK;
+}
+
+// streams (from the per-device cache when idle ones exist), pool settings and device facts of a new handle
+static int open_device_context(scdc_handle* h, int device) {
   CU(cudaSetDevice(device));
-  std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
-  if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
   h->device = device;
-  h->one_shot = o_hint != nullptr;
-  h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
-  h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
-  h->ncols = (h->C == 2) ? 3 + h->nS : 1;
-  h->nnz = (size_t)p->colptr[h->G];
   {
     std::lock_guard<std::mutex> lock(g_devcache.mu);
     DeviceCache::Entry& e = g_devcache.entry(device);
@@ -606,8 +646,7 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     if (e.known) { h->num_sms = e.num_sms; h->smem_optin = e.smem_optin; h->mem_total = e.mem_total; }
   }
   if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  AllocScope alloc_scope(h->stream);
-  if (g_alloc_async) {  // keep freed work buffers in the device's default pool for the next call
+  if (!getenv("SCDC_NO_POOL")) {  // keep freed work buffers in the device's default pool for the next call
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
@@ -632,6 +671,60 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     DeviceCache::Entry& e = g_devcache.entry(device);
     e.known = true; e.num_sms = h->num_sms; e.smem_optin = h->smem_optin; e.mem_total = h->mem_total;
   }
+  return SCDC_OK;
+}
+
+// o_hint != NULL (one-shot path): the options of the run that follows. The cheap part of the validation has been done by
+// the caller; the O(nnz) matrix check runs on a helper thread and K1 is launched ahead, both overlapping the H2D copies.
+static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, const scdc_options* o_hint) {
+  if (!out) return fail(SCDC_EINVAL, "out is NULL");
+  *out = nullptr;
+  PhaseTimer pt;
+  int rc = o_hint ? SCDC_OK : validate_problem(p);
+  if (rc) return rc;
+  pt.lap("create: validate");
+  int matrix_rc = SCDC_OK;
+  std::string matrix_err;
+  std::thread matrix_check;
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{matrix_check};
+  std::atomic<int> genes_valid{0};
+  std::atomic<bool> matrix_done{false};
+  if (o_hint) {
+    // detection mode consumes the matrix chunk by chunk behind a progress counter (sequential scan); differential mode only
+    // needs the verdict, so the scan is split over a few threads
+    auto check = [&, p]() {
+      matrix_rc = (p->n_conditions == 1) ? validate_matrix(p, &genes_valid) : validate_matrix(p, nullptr, 4);
+      if (matrix_rc) matrix_err = g_err;
+      matrix_done.store(true, std::memory_order_release);
+    };
+    try {
+      matrix_check = std::thread(check);
+    } catch (...) {
+      check();  // no thread available: validate here, before the upload
+    }
+  }
+  std::vector<int> ids;
+  if (count_sm100_devices(&ids) == 0)
+    return fail(SCDC_ENOGPU, "no visible CUDA device with compute capability 10.x (B200); there is no CPU fallback");
+  if (device < 0) device = ids[0];
+  if (std::find(ids.begin(), ids.end(), (int)device) == ids.end())
+    return fail(SCDC_ENOGPU, "device %d is not a visible compute-capability-10.x device", device);
+  const double t0 = now_ms(), h2d0 = g_h2d_bytes;
+  CU(cudaSetDevice(device));
+  std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
+  if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
+  h->device = device;
+  h->one_shot = o_hint != nullptr;
+  h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
+  h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
+  h->ncols = (h->C == 2) ? 3 + h->nS : 1;
+  h->nnz = (size_t)p->colptr[h->G];
+  rc = open_device_context(h.get(), device);
+  if (rc) return rc;
+  AllocScope alloc_scope(h->stream);
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K;
   cudaStream_t s = h->stream;
   try {
@@ -712,6 +805,14 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     // active genes. They are launched now; the pass-1 copy of the matrix and the rows are built and uploaded on the copy
     // stream (and allocated in its order) while that kernel runs. run_device then skips batch 0's k_scatter.
     cudaStream_t s_up = s;
+    cudaEvent_t ev_matrix;   // the matrix, the labels and the small tables are on the device
+    CU(cudaEventCreateWithFlags(&ev_matrix, cudaEventDisableTiming));
+    struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } ev_matrix_del{ev_matrix};
+    CU(cudaEventRecord(ev_matrix, s));
+    cudaEvent_t ev_sort;     // the pass-1 copy is built (when it was built on another stream)
+    CU(cudaEventCreateWithFlags(&ev_sort, cudaEventDisableTiming));
+    EvDel ev_sort_del{ev_sort};
+    bool sort_pending = false;
     if (o_hint && C == 2 && h->pre.valid && !o_hint->return_distributions && !env_int("SCDC_NO_EARLY_REDUCE", 0) &&
         p->n_rows > 0) {
       h->R = p->n_rows;
@@ -721,48 +822,24 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       if (rc) return rc;
       if (h->pre.k2_done) s_up = h->stream_score;
     }
-    AllocScope up_scope(s_up);
-    std::vector<int> segptr;
-    std::unique_ptr<int[]> rows_s;        // not value-initialised: the worker threads first-touch their own ranges
-    std::unique_ptr<double[]> vals_s;
     if (C == 2) {
-      // pass-1 copy of the matrix: inside each gene column, entries stably sorted by cell type
-      segptr.resize((size_t)G * (T + 1));
-      rows_s.reset(new int[h->nnz ? h->nnz : 1]);
-      vals_s.reset(new double[h->nnz ? h->nnz : 1]);
-      // host threads over contiguous gene ranges of about equal nnz (the counting sort is O(nnz) with random ct lookups)
-      const int n_thr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-      std::vector<std::thread> workers;
-      int g_lo = 0;
-      for (int w = 0; w < n_thr; ++w) {
-        const long long target = (long long)h->nnz * (w + 1) / n_thr;
-        int g_hi = g_lo;
-        while (g_hi < G && (w == n_thr - 1 || p->colptr[g_hi + 1] <= target)) ++g_hi;
-        workers.emplace_back([&, g_lo, g_hi]() {
-          std::vector<int> cnt(T + 1);
-          for (int g = g_lo; g < g_hi; ++g) {
-            const int b = p->colptr[g], e = p->colptr[g + 1];
-            std::fill(cnt.begin(), cnt.end(), 0);
-            for (int i = b; i < e; ++i) ++cnt[ct8[p->rowidx[i]] + 1];
-            int* sp = &segptr[(size_t)g * (T + 1)];
-            sp[0] = b;
-            for (int t = 0; t < T; ++t) sp[t + 1] = sp[t] + cnt[t + 1];
-            for (int t = 0; t < T; ++t) cnt[t] = sp[t];
-            for (int i = b; i < e; ++i) {
-              const int dst = cnt[ct8[p->rowidx[i]]]++;
-              rows_s[dst] = p->rowidx[i];
-              vals_s[dst] = p->values[i];
-            }
-          }
-        });
-        g_lo = g_hi;
+      // pass-1 copy of the matrix (inside each gene column, entries stably sorted by cell type), built on the device from
+      // the CSC that is already there: no host sort, no second H2D of the matrix. With batch 0's scatter already running on
+      // the compute stream, the sort goes to the high-priority label stream (idle by now: the labels were drawn during the
+      // matrix upload), so that its few blocks are scheduled at once next to the scatter's; the rows' pageable copies
+      // below use the third stream and do not queue behind it.
+      cudaStream_t s_sort = (s_up != s) ? h->stream_labels : s;
+      AllocScope sort_scope(s_sort);
+      if (s_sort != s) CU(cudaStreamWaitEvent(s_sort, ev_matrix, 0));
+      rc = build_pass1_copy(h.get(), s_sort);
+      if (rc) return rc;
+      if (s_sort != s) {
+        CU(cudaEventRecord(ev_sort, s_sort));
+        CU(cudaStreamWaitEvent(s, ev_sort, 0));  // everything later on the compute stream sees the pass-1 copy
+        sort_pending = true;
       }
-      for (auto& t : workers) t.join();
-      CU(h->segptr.upload(segptr.data(), segptr.size(), s_up));
-      pt.lap("create: pass-1 copy built");
-      CU(upload_big(h->rowidx_s, rows_s.get(), h->nnz, s_up));
-      CU(upload_big(h->values_s, vals_s.get(), h->nnz, s_up));
     }
+    AllocScope up_scope(s_up);
     pt.lap("create: pass-1 matrix copy");
     if (!rows_installed) {
       // s_up != s: everything queued on the copy stream so far is covered by the event install_rows records at its end
@@ -771,13 +848,21 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     }
     CU(h->flag.alloc(1));
     pt.lap("create: enqueue rest");
-    if (s_up != s) CU(cudaStreamSynchronize(s_up));
-    CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+    if (s_up != s) {
+      // Batch 0's scatter is still running on the compute stream: do not wait for it. Everything that read host staging
+      // memory on that stream was enqueued before ev_matrix; the rows went through the copy stream.
+      CU(cudaStreamSynchronize(s_up));
+      CU(cudaEventSynchronize(ev_matrix));
+      if (sort_pending) CU(cudaEventSynchronize(ev_sort));
+    } else {
+      CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+    }
     pt.lap("create: wait for H2D");
   } catch (const std::bad_alloc&) {
     return fail(SCDC_ENOMEM, "host allocation failed while staging the problem");
   }
   h->ms_upload = now_ms() - t0;
+  h->h2d_bytes = g_h2d_bytes - h2d0;
   *out = h.release();
   return SCDC_OK;
 }
@@ -799,6 +884,15 @@ cudaError_t launch_draw_ng(const scdc_handle* h, cudaStream_t s, uint64_t seed, 
   }
   kern<<<B / 32, 32, smem, s>>>(h->N, h->T, h->C, h->C == 2 ? h->visit.p : nullptr, h->ct_seg.p, h->expect.p, seed, perm0, Bb, J,
                                bits1, lab2, dbg_cond, dbg_ct);
+  return cudaGetLastError();
+}
+
+// The generators write the pass-1 condition bits as one word per 32 replicates; k_pass1_cond reads them byte-packed per
+// lane (k_bits_transpose8, in place). B replicates in blocks of Bb (a multiple of 256 whenever pass 1 runs).
+cudaError_t repack_condition_bits(const scdc_handle* h, cudaStream_t s, uint32_t* bits1, int64_t B, int Bb) {
+  if (Bb % 256 != 0) return cudaSuccess;  // debug draws (scdc_draw_labels): the words are never consumed
+  const size_t n_groups = (size_t)h->N * (size_t)(B / 256);
+  if (n_groups) scdc::k_bits_transpose8<<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(n_groups, bits1);
   return cudaGetLastError();
 }
 
@@ -856,27 +950,35 @@ cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t p
       scdc::k_relayout_labels<<<grid, 256, 0, s>>>(N, Bb, J, out + (size_t)b0 * N, lab2 + (size_t)b0 * N, keys2 ? T : 0,
                                                    keys2 ? bits1 + (size_t)b0 / 32 * N : nullptr);
     }
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && keys2) e = repack_condition_bits(h, s, bits1, B, Bb);
+    return e;
   }
-  if (T <= 16) return launch_draw_ng<2>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 32) return launch_draw_ng<4>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 64) return launch_draw_ng<8>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
-  if (T <= 128) return launch_draw_ng<16>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
-  return launch_draw_ng<32>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  cudaError_t e;
+  if (T <= 16) e = launch_draw_ng<2>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  else if (T <= 32) e = launch_draw_ng<4>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  else if (T <= 64) e = launch_draw_ng<8>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  else if (T <= 128) e = launch_draw_ng<16>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  else e = launch_draw_ng<32>(h, s, seed, perm0, B, Bb, J, bits1, lab2, dbg_cond, dbg_ct);
+  if (e == cudaSuccess && h->C == 2 && !dbg_ct && !dbg_cond) e = repack_condition_bits(h, s, bits1, B, Bb);
+  return e;
 }
 
 struct ScatterPlan {
   int J, W, blocks_per_sm;
   size_t smem;
+  bool f32;
 };
 
-ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
+// f32 (SCDC_FP32_FAST): fp32 accumulators are half the size, so twice the replicates per lane fit the same footprint
+ScatterPlan plan_scatter(const scdc_handle* h, int Bpad, bool f32) {
   const int K = h->K;
-  int J = (K <= 16) ? 4 : (K <= 32 ? 2 : 1);
-  J = env_int("SCDC_J", J);
+  const size_t vs = f32 ? 4 : 8, es = f32 ? 8 : 16;  // bytes per accumulator / per staged entry
+  int J = f32 ? ((K <= 32) ? 4 : (K <= 64 ? 2 : 1)) : ((K <= 16) ? 4 : (K <= 32 ? 2 : 1));
+  J = env_int(f32 ? "SCDC_J32" : "SCDC_J", J);
   if (J != 1 && J != 2 && J != 4) J = 1;
   while (J > 1 && (Bpad % (32 * J)) != 0) J >>= 1;
-  const size_t per_warp = (size_t)K * J * 256 + 1024;
+  const size_t per_warp = (size_t)K * J * 32 * vs + 64 * es;
   const int nCJ = Bpad / (32 * J);
   const size_t cap = h->smem_optin ? h->smem_optin : 232448;
   int bestW = 1, best_warps = 0, best_bps = 1;
@@ -891,40 +993,78 @@ ScatterPlan plan_scatter(const scdc_handle* h, int Bpad) {
   int W = env_int("SCDC_W", bestW);
   if (W < 1 || W > 32 || per_warp * W > cap) W = bestW;
   ScatterPlan pl;
-  pl.J = J; pl.W = W; pl.blocks_per_sm = best_bps; pl.smem = per_warp * W;
+  pl.J = J; pl.W = W; pl.blocks_per_sm = best_bps; pl.smem = per_warp * W; pl.f32 = f32;
   return pl;
 }
 
-template <int J, int U, bool PAIR>
+template <typename VT> const VT* matrix_values(const scdc_handle* h);
+template <> const double* matrix_values<double>(const scdc_handle* h) { return h->values.p; }
+template <> const float* matrix_values<float>(const scdc_handle* h) { return h->values_f.p; }
+
+template <typename VT, int J, int U, bool PAIR>
 cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                             double* M2, cudaStream_t s, const int* genes, int n_genes) {
-  auto kern = scdc::k_scatter<J, U, PAIR>;
+                             void* M2, cudaStream_t s, const int* genes, int n_genes) {
+  auto kern = scdc::k_scatter<VT, J, U, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
   dim3 grid(n_genes, (nCJ + pl.W - 1) / pl.W);  // active genes only (gene_order, or one upload chunk of it)
-  kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, h->values.p, lab2, lab_stride,
-                                        h->ngroup.p, genes, M2);
+  kern<<<grid, pl.W * 32, pl.smem, s>>>(h->G, h->K, nCJ, h->colptr.p, h->rowidx.p, matrix_values<VT>(h), lab2, lab_stride,
+                                        h->ngroup.p, genes, static_cast<VT*>(M2));
   return cudaGetLastError();
 }
 
-template <int J>
+template <typename VT, int J>
+cudaError_t launch_scatter_j(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
+                             void* M2, cudaStream_t s, const int* genes, int n_genes) {
+  if constexpr (J == 1) {
+    // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
+    const int warps_per_sm = pl.blocks_per_sm * pl.W;
+    const int U = env_int("SCDC_U", (warps_per_sm <= 8) ? 16 : 8);
+    const int pair = env_int("SCDC_PAIR", (warps_per_sm <= 8) ? 1 : 0);
+    if (U == 16 && pair) return launch_scatter_u<VT, 1, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    if (U == 16) return launch_scatter_u<VT, 1, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    if (pair) return launch_scatter_u<VT, 1, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    return launch_scatter_u<VT, 1, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  } else {
+    return launch_scatter_u<VT, J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  }
+}
+
+// pass-2 group sums of one batch: plan -> kernel instance (value type, replicates per lane, prefetch depth, pair mode)
 cudaError_t launch_scatter(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
-                           double* M2, cudaStream_t s, const int* genes = nullptr, int n_genes = -1) {
+                           void* M2, cudaStream_t s, const int* genes = nullptr, int n_genes = -1) {
   if (!genes) { genes = h->gene_order.p; n_genes = h->n_active; }
   if (n_genes <= 0) return cudaSuccess;
-  // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
-  const int warps_per_sm = pl.blocks_per_sm * pl.W;
-  const int U = env_int("SCDC_U", (J == 1 && warps_per_sm <= 8) ? 16 : 8);
-  const int pair = env_int("SCDC_PAIR", (J == 1 && warps_per_sm <= 8) ? 1 : 0);
-  if (J == 1 && U == 16 && pair) return launch_scatter_u<J, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-  if (J == 1 && U == 16) return launch_scatter_u<J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-  if (J == 1 && pair) return launch_scatter_u<J, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-  return launch_scatter_u<J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  if (pl.f32) {
+    if (pl.J == 4) return launch_scatter_j<float, 4>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    if (pl.J == 2) return launch_scatter_j<float, 2>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    return launch_scatter_j<float, 1>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  }
+  if (pl.J == 4) return launch_scatter_j<double, 4>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  if (pl.J == 2) return launch_scatter_j<double, 2>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+  return launch_scatter_j<double, 1>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+}
+
+// SCDC_FP32_FAST: fp32 copies of the matrix values (pass 2) / of the pass-1 records, made on the device once per handle
+// (enqueued on `s`, which must be ordered after the fp64 originals)
+int ensure_f32_values(scdc_handle* h, cudaStream_t s, bool pass1) {
+  const size_t n = h->nnz, need = std::max<size_t>(n, 1);
+  if (pass1) {
+    if (h->rec_sf.p && h->rec_sf.n >= need) return SCDC_OK;
+    CU(h->rec_sf.alloc(need));
+    if (n) scdc::k_rec_to_float<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->rec_s.p, h->rec_sf.p);
+  } else {
+    if (h->values_f.p && h->values_f.n >= need) return SCDC_OK;
+    CU(h->values_f.alloc(need));
+    if (n) scdc::k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->values.p, h->values_f.p);
+  }
+  CU(cudaGetLastError());
+  return SCDC_OK;
 }
 
 int pick_batch(const scdc_handle* h, const scdc_options* o) {
-  const double per_perm = (double)h->C * h->G * h->K * 8.0 + (double)h->N * 1.125 +
+  const double per_perm = (double)h->C * h->G * h->K * (o->precision == SCDC_FP32_FAST ? 4.0 : 8.0) + (double)h->N * 1.125 +
                           ((o->perm_ct != nullptr) ? 2.0 * h->N : 0.0) +
                           (o->return_distributions ? (double)h->R * ((h->C == 2) ? 3 : 1) * 8.0 : 0.0);
   double budget = std::min((double)h->mem_total * 0.25, 24.0e9);
@@ -934,14 +1074,22 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
   // efficient than the monolithic launch, so only about a third of the work should go that way.
   B = std::min<long long>(B, std::max(128, env_int("SCDC_BMAX", (h->one_shot && h->C == 1) ? 4096 : 16384)));
   if (o->batch_size > 0) B = o->batch_size;
-  B = std::max<long long>(128, (B / 128) * 128);
+  const long long q = (h->C == 2) ? 256 : 128;  // granularity: k_pass1_cond covers 256 replicates per warp, k_scatter 128
+  B = std::max<long long>(q, (B / q) * q);
   if (o->batch_size <= 0) {
-    // equal batches: the reduction always runs whole batches, so ceil(iterations / B) batches of the smallest multiple
-    // of 128 that covers them wastes at most 127 replicates per batch (10 000 -> 3 x 3456 instead of 3 x 4096)
-    const long long nbat = (o->iterations + B - 1) / B;
-    B = std::min<long long>(B, (((o->iterations + nbat - 1) / nbat + 127) / 128) * 128);
+    // equal batches: the reduction always runs whole batches, so n batches of the smallest multiple of q that covers
+    // iterations / n waste at most q - 1 replicates per batch (10 000 -> 1 x 10 112 instead of 3 x 4096); among the batch
+    // counts that fit the memory budget (and up to twice the minimum) take the one that pads least
+    const long long n_min = (o->iterations + B - 1) / B;
+    long long best_B = 0, best_total = 0;
+    for (long long n = n_min; n <= 2 * n_min; ++n) {
+      const long long Bn = (((o->iterations + n - 1) / n + q - 1) / q) * q;
+      if (Bn > B) continue;
+      if (!best_B || n * Bn < best_total) { best_B = Bn; best_total = n * Bn; }
+    }
+    if (best_B) B = best_B;
   } else {
-    B = std::min<long long>(B, ((o->iterations + 127) / 128) * 128);
+    B = std::min<long long>(B, ((o->iterations + q - 1) / q) * q);
   }
   return (int)B;
 }
@@ -963,7 +1111,7 @@ int64_t pick_super_batch(const scdc_handle* h, const scdc_options* o, int B) {
 int prelaunch_labels(scdc_handle* h, const scdc_options* o) {
   if (o->perm_ct != nullptr || env_int("SCDC_NO_PRELAUNCH", 0)) return SCDC_OK;
   const int B = pick_batch(h, o);
-  const ScatterPlan pl = plan_scatter(h, B);
+  const ScatterPlan pl = plan_scatter(h, B, o->precision == SCDC_FP32_FAST);
   const int64_t SB = pick_super_batch(h, o, B);
   CU(h->lab2[0].ensure((size_t)h->N * SB));
   if (h->C == 2) CU(h->bits1[0].ensure((size_t)h->N * (SB / 32)));
@@ -989,7 +1137,8 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
   cudaStream_t s = h->stream;
   const int G = h->G, K = h->K;
   const int B = pick_batch(h, o);
-  const ScatterPlan pl = plan_scatter(h, B);
+  const bool f32 = o->precision == SCDC_FP32_FAST;
+  const ScatterPlan pl = plan_scatter(h, B, f32);
   if (pl.J != h->pre.J) {  // cannot happen (same planning inputs); fall back to the plain copy
     CU(upload_big(h->rowidx, p->rowidx, h->nnz, s));
     CU(upload_big(h->values, p->values, h->nnz, s));
@@ -997,6 +1146,7 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
   }
   CU(h->rowidx.alloc(h->nnz));
   CU(h->values.alloc(h->nnz));
+  if (f32) CU(h->values_f.alloc(h->nnz ? h->nnz : 1));
   CU(h->M2[0].ensure((size_t)(B / 32) * G * K * 32));
   // chunks: contiguous gene ranges of about equal nnz
   const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(16, h->nnz / (size_t)std::max(1, env_int("SCDC_CHUNK_NNZ", 1 << 19))));
@@ -1038,6 +1188,7 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
       // slower per call than the driver's own staging of these 3-5 MB pieces on an idle host)
       CU(cudaMemcpyAsync(h->rowidx.p + e0, p->rowidx + e0, (e1 - e0) * sizeof(int), cudaMemcpyHostToDevice, sc));
       CU(cudaMemcpyAsync(h->values.p + e0, p->values + e0, (e1 - e0) * sizeof(double), cudaMemcpyHostToDevice, sc));
+      g_h2d_bytes += (double)(e1 - e0) * 12.0;
     }
     // chunk kernels alternate between two streams so that the tail of one chunk overlaps the head of the next
     cudaStream_t sk = (c & 1) ? h->stream_labels : s;
@@ -1053,10 +1204,9 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
       first = false;
     }
     const int n_g = off[c + 1] - off[c];
-    cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g)
-                     : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g)
-                                   : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g);
-    CU(le);
+    if (f32 && e1 > e0)  // this chunk's fp32 values
+      scdc::k_to_float<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, sk>>>(e1 - e0, h->values.p + e0, h->values_f.p + e0);
+    CU(launch_scatter(h, pl, B, h->lab2[0].p, B, h->M2[0].p, sk, d_list.p + off[c], n_g));
   }
   if (first) CU(cudaEventRecord(h->pre.k2_t0, s));
   CU(cudaEventRecord(copied, h->stream_labels));  // join the second kernel stream
@@ -1073,16 +1223,18 @@ int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, co
 int launch_early_scatter(scdc_handle* h, const scdc_options* o) {
   cudaStream_t s = h->stream;
   const int B = pick_batch(h, o);
-  const ScatterPlan pl = plan_scatter(h, B);
+  const bool f32 = o->precision == SCDC_FP32_FAST;
+  const ScatterPlan pl = plan_scatter(h, B, f32);
   if (pl.J != h->pre.J || h->n_active == 0) return SCDC_OK;  // (cannot happen / nothing to reduce): the normal path runs
+  if (f32) {
+    int rc = ensure_f32_values(h, s, false);
+    if (rc) return rc;
+  }
   CU(h->M2[0].ensure((size_t)(B / 32) * h->G * h->K * 32));
   if (!h->pre.k2_t0) { CU(cudaEventCreate(&h->pre.k2_t0)); CU(cudaEventCreate(&h->pre.k2_t1)); }
   CU(cudaStreamWaitEvent(s, h->pre.t1, 0));  // labels of super-batch 0
   CU(cudaEventRecord(h->pre.k2_t0, s));
-  cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s)
-                   : (pl.J == 2) ? launch_scatter<2>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s)
-                                 : launch_scatter<1>(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s);
-  CU(le);
+  CU(launch_scatter(h, pl, B, h->lab2[0].p, B, h->M2[0].p, s));
   CU(cudaEventRecord(h->pre.k2_t1, s));
   h->pre.k2_done = true;
   h->pre.B = B;
@@ -1098,7 +1250,9 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K, R = h->R;
   const int B = pick_batch(h, o);
   const int Bw = B / 32;
-  const ScatterPlan pl = plan_scatter(h, B);
+  const bool f32 = o->precision == SCDC_FP32_FAST;
+  const double rel_tol = (o->rel_tol > 0.0) ? o->rel_tol : 1e-5;
+  const ScatterPlan pl = plan_scatter(h, B, f32);
   const bool uploaded = o->perm_ct != nullptr;
   // Device-drawn labels: K1 is one thread per replicate and sequential over the cells, so its run time hardly depends on
   // how many replicates it draws. It therefore draws a whole SUPER-batch (SB replicates, as many as the label memory cap
@@ -1131,6 +1285,12 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(h->M2[i].ensure(msz));
   }
   CU(h->counts.ensure((size_t)R * h->ncols + 1));
+  if (f32) {
+    CU(h->band.ensure((size_t)R * h->ncols + 1));
+    int rc = ensure_f32_values(h, h->stream, false);
+    if (!rc && C == 2) rc = ensure_f32_values(h, h->stream, true);
+    if (rc) return rc;
+  }
   if (uploaded) {
     CU(h->up_ct.ensure((size_t)B * N));
     if (C == 2) CU(h->up_cond.ensure((size_t)B * N));
@@ -1144,6 +1304,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(e1); CU(e2);
   }
   CU(cudaMemsetAsync(h->counts.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
+  if (f32) CU(cudaMemsetAsync(h->band.p, 0, ((size_t)R * h->ncols + 1) * sizeof(uint32_t), s));
   if (uploaded) CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
   std::vector<cudaEvent_t> evs, evl;  // timing events on the compute stream (3 per batch) / label stream (2 per batch)
   auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st_) -> cudaError_t {
@@ -1193,7 +1354,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   }
   int64_t launches = 0, reduce_launches = 0;
   double reduce_bytes = 0, reduce_wavefronts = 0;
-  const double sv = 8.0;
+  const double sv = f32 ? 4.0 : 8.0;
   CU(mark(evs, s));  // evs[0]: start of the whole loop on the compute stream
   auto issue_labels = [&](int64_t sb_start, int buf) -> int {
     if (pipelined && freed_set[buf]) CU(cudaStreamWaitEvent(sL, freed[buf], 0));
@@ -1264,12 +1425,14 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(cudaMemcpyAsync(h->up_ct.p, o->perm_ct + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
       if (C == 2)
         CU(cudaMemcpyAsync(h->up_cond.p, o->perm_cond + (size_t)done * N, (size_t)nb * N, cudaMemcpyHostToDevice, s));
+      g_h2d_bytes += (double)nb * N * C;
       scdc::k_check_uploaded<<<nb, 256, 2 * K * sizeof(int), s>>>(N, T, C, h->ct.p, h->up_cond.p, h->up_ct.p, h->expect.p,
                                                                   h->flag.p);
       dim3 grid((N + 31) / 32, B / 32), block(32, 32);
       scdc::k_pack_uploaded<<<grid, block, 0, s>>>(N, T, C, nb, B, pl.J, h->ct.p, h->cond.p, h->up_cond.p, h->up_ct.p,
                                                    h->bits1[0].p, h->lab2[0].p);
       CU(cudaGetLastError());
+      if (C == 2) CU(repack_condition_bits(h, s, h->bits1[0].p, B, B));
       CU(mark(evl, s));
       launches += 2;
     } else if (in_sb == 0) {
@@ -1291,10 +1454,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       }
     }
     const uint8_t* lab2_b = h->lab2[buf].p + (size_t)in_sb * N;                      // block [in_sb / B]: [cell][B] bytes
-    const uint32_t* bits1_b = (C == 2) ? h->bits1[buf].p + (size_t)(in_sb / 32) * N : nullptr;  // [cell][B / 32] words
+    const uint8_t* bits1_b =   // [cell][B / 8] bytes (k_bits_transpose8)
+        (C == 2) ? reinterpret_cast<const uint8_t*>(h->bits1[buf].p + (size_t)(in_sb / 32) * N) : nullptr;
     const int mb = overlap_score ? (int)((done / B) & 1) : 0;  // group-means buffer of this batch
-    double* M1b = h->M1[mb].p;
-    double* M2b = h->M2[mb].p;
+    void* M1b = h->M1[mb].p;   // element type: double, or float in SCDC_FP32_FAST (half of the buffer used)
+    void* M2b = h->M2[mb].p;
     if (overlap_score && m_free_set[mb]) CU(cudaStreamWaitEvent(s, m_free[mb], 0));  // K3 of batch b-2 has read it
     CU(mark(evs, s));
     // Pass 1 (issue-slot bound, little shared memory) can run NEXT TO the pass-2 scatter (shared-memory-pipe bound): it is
@@ -1302,19 +1466,24 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     // scatter leaves free on every SM, and joined before K3.
     const int ov1 = (C == 2) ? env_int("SCDC_OVERLAP_PASS1", 1) : 0;
     auto launch_pass1 = [&](cudaStream_t sp, int W) -> cudaError_t {
-      const int nWC = B / 128;
+      const int nWC = B / 256;
       const long long tasks = (long long)h->n_active * nWC;
       const unsigned grid1 = (unsigned)((tasks + W - 1) / W);
-      if (env_int("SCDC_U1", 4) == 4)  // 80 registers, 3 blocks / SM; U = 8 (144 registers, 1 block) measured slower
-        scdc::k_pass1_cond<4><<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
-                                                        h->ngroup.p, h->gene_order.p, M1b);
-      else
-        scdc::k_pass1_cond<8><<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, h->rowidx_s.p, h->values_s.p, bits1_b, Bw,
-                                                        h->ngroup.p, h->gene_order.p, M1b);
+      const int U1 = env_int("SCDC_U1", 4);  // records per pipeline stage
+      auto go = [&](auto kern, auto* rec, auto* M1t) {
+        kern<<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p, M1t);
+      };
+      if (f32) {
+        if (U1 == 2) go(scdc::k_pass1_cond<float, 2>, h->rec_sf.p, static_cast<float*>(M1b));
+        else go(scdc::k_pass1_cond<float, 4>, h->rec_sf.p, static_cast<float*>(M1b));
+      } else {
+        if (U1 == 2) go(scdc::k_pass1_cond<double, 2>, h->rec_s.p, static_cast<double*>(M1b));
+        else go(scdc::k_pass1_cond<double, 4>, h->rec_s.p, static_cast<double*>(M1b));
+      }
       return cudaGetLastError();
     };
     if (C == 2 && !ov1) {
-      CU(launch_pass1(s, 8));
+      CU(launch_pass1(s, 4));
       ++launches; ++reduce_launches;
     }
     if (C == 2 && ov1) CU(cudaEventRecord(ov_fork, s));  // labels, means buffers and everything before are ready
@@ -1322,10 +1491,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       launches += h->pre.k2_launches;  // batch 0 was reduced behind the matrix upload (upload_matrix_with_early_reduction)
       reduce_launches += h->pre.k2_launches;
     } else {
-      cudaError_t le = (pl.J == 4)   ? launch_scatter<4>(h, pl, B, lab2_b, B, M2b, s)
-                       : (pl.J == 2) ? launch_scatter<2>(h, pl, B, lab2_b, B, M2b, s)
-                                     : launch_scatter<1>(h, pl, B, lab2_b, B, M2b, s);
-      CU(le);
+      CU(launch_scatter(h, pl, B, lab2_b, B, M2b, s));
       ++launches; ++reduce_launches;
     }
     if (C == 2 && ov1) {
@@ -1340,9 +1506,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
                     (double)B * N * (C == 2 ? 1.125 : 1.0) + (double)C * B * K * h->n_active * sv;
     // shared-memory wavefronts by design: per (entry x 32J replicates) the scatter issues a 2-wavefront entry broadcast,
-    // J x (LDS.64 + STS.64) = 4J and 4/32 for the staging store; pass 1 only the broadcast and the staging store
-    reduce_wavefronts += (double)h->nnz_active * (B / (32.0 * pl.J)) * (2.0 + 4.0 * pl.J + 0.125) +
-                         (C == 2 ? (double)h->nnz_active * (B / 128.0) * 2.125 : 0.0);
+    // J x (LDS.64 + STS.64) = 4J and 4/32 for the staging store; pass 1 only the broadcast and the staging store.
+    // fp32: 1-wavefront broadcast (LDS.64), J x (LDS.32 + STS.32) = 2J, 2/32 for the staging store.
+    const double wf_b = f32 ? 1.0 : 2.0, wf_rmw = f32 ? 2.0 : 4.0, wf_st = f32 ? 0.0625 : 0.125;
+    reduce_wavefronts += (double)h->nnz_active * (B / (32.0 * pl.J)) * (wf_b + wf_rmw * pl.J + wf_st) +
+                         0.0;  // pass 1 (k_pass1_cond) uses no shared memory
     CU(mark(evs, s));
     if (overlap_score) {
       CU(cudaEventRecord(m_ready[mb], s));
@@ -1351,12 +1519,17 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     }
     if (R > 0 && !dist_host && !env_int("SCDC_SCORE_V1", 0)) {
       const int Tp = T | 1;
-      const int n_arr = (C == 2) ? 16 + h->nS : 4;  // RAW tiles double-buffered (2 x 8 | 2 x 2) + D tiles
+      // shared memory of the production score kernels, in doubles per replicate of a tile: RAW tiles double-buffered
+      // (differential 2 x 2 sides x 4 values, detection 2 x 2 sides x 1), + the subunit-difference tiles when the subunit
+      // columns are not factorised
+      const bool fact = C == 2 && h->fact_ok;
+      const int n_arr = (C == 2) ? (f32 ? 8 : 16) + (fact ? 0 : h->nS * (f32 ? 2 : 1)) : (f32 ? 2 : 4);
+      const size_t tail = fact ? (size_t)T * h->nS * 8 + (size_t)T * h->nS * 4 * (f32 ? 2 : 1) + 8 : 0;
       int P = 32;
       const size_t smem_target = (size_t)env_int("SCDC_SCORE_SMEM_KB", 100) * 1024;
-      while (P > 4 && (size_t)n_arr * P * Tp * 8 > smem_target) P >>= 1;
+      while (P > 4 && (size_t)n_arr * P * Tp * 8 + tail > smem_target) P >>= 1;
       P = env_int("SCDC_SCORE_P", P);
-      const size_t smem = (size_t)n_arr * P * Tp * 8;
+      const size_t smem = (size_t)n_arr * P * Tp * 8 + tail;
       if (C == 2) {
         scdc::ScoreDiffArgs D;
         D.G = G; D.T = T; D.Tp = Tp; D.K = K; D.nL = h->nL; D.nR = h->nR; D.score_type = o->score_type;
@@ -1364,42 +1537,48 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
         D.task_lri = h->task_lri.p; D.task_beg = h->task_beg.p; D.task_end = h->task_end.p; D.srow = h->srow.p;
         D.sub_gene = h->sub_gene.p; D.row_emit = h->row_emit.p; D.row_recv = h->row_recv.p; D.obs = h->obs.p;
         D.thr = h->thr.p; D.obs_sub = h->obs_sub.p; D.M1 = M1b; D.M2 = M2b; D.counts = h->counts.p;
-        if (h->fact_ok) {
-          auto kern = scdc::k_score_diff<kScoreRPT, true>;
-          CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D.band = h->band.p; D.rel_tol = rel_tol;
+        auto go = [&](auto kern) -> cudaError_t {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
           kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
-        } else {
-          auto kern = scdc::k_score_diff<kScoreRPT, false>;
-          CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
-        }
+          return cudaGetLastError();
+        };
+        if (f32) CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, float, true>) : go(scdc::k_score_diff<kScoreRPT, false, float, true>));
+        else CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, double, false>) : go(scdc::k_score_diff<kScoreRPT, false, double, false>));
       } else {
         scdc::ScoreDetArgs A;
         A.G = G; A.T = T; A.Tp = Tp; A.nL = h->nL; A.nS = h->nS; A.score_type = o->score_type;
         A.n_valid = nb; A.P = P; A.R = R;
         A.task_lri = h->task_lri.p; A.task_beg = h->task_beg.p; A.task_end = h->task_end.p; A.srow = h->srow.p;
         A.sub_gene = h->sub_gene.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p; A.obs = h->obs.p;
-        A.thr = h->thr.p; A.M2 = M2b; A.counts = h->counts.p;
-        auto kern = scdc::k_score_det<kScoreRPT>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
+        A.thr = h->thr.p; A.M2 = M2b; A.counts = h->counts.p; A.band = h->band.p; A.rel_tol = rel_tol;
+        auto go = [&](auto kern) -> cudaError_t {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+          kern<<<h->n_tasks, h->score_threads, smem, sS>>>(A);
+          return cudaGetLastError();
+        };
+        CU(f32 ? go(scdc::k_score_det<kScoreRPT, float, true>) : go(scdc::k_score_det<kScoreRPT, double, false>));
       }
-      CU(cudaGetLastError());
       ++launches;
     } else if (R > 0) {
       scdc::ScoreArgs A;
       A.R = R; A.G = G; A.T = T; A.C = C; A.nL = h->nL; A.nR = h->nR; A.ncols = h->ncols; A.score_type = o->score_type;
       A.nChunks = (nb + 31) / 32; A.n_valid = nb;
       A.sub_gene = h->sub_gene.p; A.row_lri = h->row_lri.p; A.row_emit = h->row_emit.p; A.row_recv = h->row_recv.p;
-      A.obs = h->obs.p; A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p;
+      A.obs = h->obs.p; A.M1 = M1b; A.M2 = M2b; A.counts = h->counts.p; A.band = h->band.p; A.rel_tol = rel_tol;
       A.dist = dist_host ? h->dist.p : nullptr;
       const int blocks = std::max(1, std::min((R + 7) / 8, h->num_sms * 8));
-      scdc::k_score_count<<<blocks, 256, 0, sS>>>(A);
+      if (f32) scdc::k_score_count<float, true><<<blocks, 256, 0, sS>>>(A);
+      else scdc::k_score_count<double, false><<<blocks, 256, 0, sS>>>(A);
       CU(cudaGetLastError());
       ++launches;
-      if (dist_host)
+      if (dist_host) {
         CU(cudaMemcpyAsync(dist_host + (size_t)done * ncols_d * R, h->dist.p, (size_t)nb * ncols_d * R * sizeof(double),
                            cudaMemcpyDeviceToHost, sS));
+        g_d2h_bytes += (double)nb * ncols_d * R * sizeof(double);
+      }
     }
     if (overlap_score) {
       CU(mark(evk, sS));
@@ -1474,23 +1653,45 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   return SCDC_OK;
 }
 
-int finish_counts(const scdc_handle* h, const std::vector<long long>& raw, uint64_t* out) {
+// uint32 device counters -> the caller's uint64 array with the NA marks (a few host threads on large tables)
+int counts_to_host(const scdc_handle* h, const uint32_t* dev, uint64_t* out) {
   const size_t n = (size_t)h->R * h->ncols;
-  for (size_t i = 0; i < n; ++i) out[i] = h->obs_na[i] ? SCDC_COUNT_NA : (uint64_t)raw[i];
+  if (!n) return SCDC_OK;
+  std::unique_ptr<uint32_t[]> raw32(new (std::nothrow) uint32_t[n]);
+  if (!raw32) return fail(SCDC_ENOMEM, "host allocation failed");
+  CU(cudaMemcpy(raw32.get(), dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  g_d2h_bytes += (double)n * sizeof(uint32_t);
+  const std::vector<uint8_t>& na = *h->obs_na;
+  const int n_thr = (n > (1u << 20)) ? 4 : 1;
+  auto body = [&](int w) {
+    const size_t lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
+    for (size_t i = lo; i < hi; ++i) out[i] = na[i] ? SCDC_COUNT_NA : (uint64_t)raw32[i];
+  };
+  std::vector<std::thread> th;
+  try {
+    for (int w = 1; w < n_thr; ++w) th.emplace_back(body, w);
+  } catch (...) {
+    for (int w = (int)th.size() + 1; w < n_thr; ++w) body(w);
+  }
+  body(0);
+  for (auto& t : th) t.join();
   return SCDC_OK;
 }
 
-// ---- NCCL, loaded lazily (only the multi-GPU merge needs it) ------------------------------------------------------
+// ---- NCCL, loaded lazily (only the multi-GPU broadcast / merge use it; without it peer copies do the same job) ------
 struct NcclApi {
   void* lib = nullptr;
+  bool tried = false;
   int (*CommInitAll)(void**, int, const int*) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
-    if (lib) return true;
+    if (tried) return lib != nullptr;
+    tried = true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
       lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -1500,15 +1701,124 @@ struct NcclApi {
     CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclBroadcast");
     GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
     GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    if (!(CommInitAll && CommDestroy && AllReduce && Broadcast && GroupStart && GroupEnd)) lib = nullptr;
+    return lib != nullptr;
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclInt64 = 4;  // ncclInt64
-constexpr int kNcclSum = 0;    // ncclSum
+std::mutex g_nccl_mu;            // one multi-GPU call at a time uses the cached communicators
+std::vector<int> g_comm_devs;    // device set of the cached communicators
+std::vector<void*> g_comms;
+constexpr int kNcclUint8 = 1, kNcclUint32 = 3;  // ncclUint8, ncclUint32
+constexpr int kNcclSum = 0;                     // ncclSum
+
+// communicators for `devs`, created once per device set and kept for the life of the process (ncclCommInitAll ~1.5 s).
+// false: NCCL is unavailable (not loadable, SCDC_NO_NCCL=1, or the init failed) and the peer-copy path is used.
+bool nccl_comms_for(const std::vector<int>& devs) {
+  if (env_int("SCDC_NO_NCCL", 0) || !g_nccl.load()) return false;
+  if (g_comm_devs == devs && !g_comms.empty()) return true;
+  for (void* c : g_comms) if (c) g_nccl.CommDestroy(c);
+  g_comms.assign(devs.size(), nullptr);
+  g_comm_devs.clear();
+  if (g_nccl.CommInitAll(g_comms.data(), (int)devs.size(), devs.data()) != 0) {
+    g_comms.clear();
+    return false;
+  }
+  g_comm_devs = devs;
+  return true;
+}
+
+// One device buffer of the root handle and its (already allocated) twins on the other devices
+struct Mirror {
+  const void* src;
+  std::vector<void*> dst;  // [W], dst[0] == src
+  size_t bytes;
+};
+
+// Copies every Mirror from device hs[0] to the devices of hs[1..]: ncclBroadcast over NVLink when NCCL is available, else
+// cudaMemcpyPeerAsync from the root. Enqueued on each twin's stream; on the root the NCCL kernels go to `root_stream`, a
+// high-priority stream of their own, because the root's compute stream is already busy with its first batch.
+int broadcast_mirrors(const std::vector<scdc_handle*>& hs, const std::vector<Mirror>& ms, bool use_nccl,
+                      cudaStream_t root_stream) {
+  const int W = (int)hs.size();
+  for (const Mirror& m : ms) {
+    if (!m.bytes) continue;
+    if (use_nccl) {
+      int nrc = g_nccl.GroupStart();
+      for (int r = 0; r < W && nrc == 0; ++r)
+        nrc = g_nccl.Broadcast(m.src, m.dst[r], m.bytes, kNcclUint8, 0, g_comms[r], r ? hs[r]->stream : root_stream);
+      const int erc = g_nccl.GroupEnd();
+      if (nrc != 0 || erc != 0)
+        return fail(SCDC_ENCCL, "ncclBroadcast failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc ? nrc : erc) : "?");
+    } else {
+      for (int r = 1; r < W; ++r)
+        CU(cudaMemcpyPeerAsync(m.dst[r], hs[r]->device, m.src, hs[0]->device, m.bytes, hs[r]->stream));
+    }
+    g_p2p_bytes += (double)m.bytes * (W - 1);
+  }
+  return SCDC_OK;
+}
+
+// The twins of a fully created handle on other devices: same problem, same rows, nothing read from the caller's host
+// arrays again. Allocates the twins' device buffers (each in its own stream's order) and fills `ms` with what to copy.
+int clone_handles(std::vector<scdc_handle*>& hs, const std::vector<int>& devs, std::vector<Mirror>& ms) {
+  scdc_handle* h0 = hs[0];
+  const int W = (int)hs.size();
+  for (int r = 1; r < W; ++r) {
+    std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
+    if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
+    int rc = open_device_context(h.get(), devs[r]);
+    if (rc) return rc;
+    h->N = h0->N; h->G = h0->G; h->T = h0->T; h->C = h0->C; h->L = h0->L; h->R = h0->R; h->nL = h0->nL; h->nR = h0->nR;
+    h->K = h0->K; h->ncols = h0->ncols; h->nS = h0->nS; h->nnz = h0->nnz;
+    h->obs_na = h0->obs_na;
+    h->fact_ok = h0->fact_ok; h->n_tasks = h0->n_tasks; h->score_threads = h0->score_threads;
+    h->sub_gene_h = h0->sub_gene_h; h->gene_nnz_h = h0->gene_nnz_h;
+    h->max_nt = h0->max_nt; h->max_nc = h0->max_nc; h->n_active = h0->n_active; h->nnz_active = h0->nnz_active;
+    h->one_shot = true;
+    hs[r] = h.release();
+  }
+  size_t idx = 0;
+  auto mirror = [&](auto member) -> int {   // member: pointer to a DBuf member of scdc_handle
+    auto& src = h0->*member;
+    if (ms.size() <= idx) ms.resize(idx + 1);
+    Mirror& m = ms[idx++];
+    m.src = src.p;
+    m.bytes = src.p ? src.n * sizeof(*src.p) : 0;
+    m.dst.assign(W, nullptr);
+    m.dst[0] = src.p;
+    for (int r = 1; r < W && m.bytes; ++r) {
+      CU(cudaSetDevice(hs[r]->device));
+      AllocScope scope(hs[r]->stream);
+      auto& d = hs[r]->*member;
+      CU(d.alloc(src.n));
+      m.dst[r] = d.p;
+    }
+    return SCDC_OK;
+  };
+#define SCDC_MIRROR(member)                      \
+  do {                                           \
+    int rc_ = mirror(&scdc_handle::member);      \
+    if (rc_) return rc_;                         \
+  } while (0)
+  SCDC_MIRROR(colptr); SCDC_MIRROR(rowidx); SCDC_MIRROR(values); SCDC_MIRROR(segptr); SCDC_MIRROR(rec_s);
+  SCDC_MIRROR(values_f); SCDC_MIRROR(rec_sf);
+  SCDC_MIRROR(gene_order); SCDC_MIRROR(sub_gene); SCDC_MIRROR(row_lri); SCDC_MIRROR(row_emit); SCDC_MIRROR(row_recv);
+  SCDC_MIRROR(ngroup); SCDC_MIRROR(obs); SCDC_MIRROR(ct); SCDC_MIRROR(cond); SCDC_MIRROR(expect); SCDC_MIRROR(visit);
+  SCDC_MIRROR(ct_seg); SCDC_MIRROR(task_lri); SCDC_MIRROR(task_beg); SCDC_MIRROR(task_end); SCDC_MIRROR(srow);
+  SCDC_MIRROR(thr); SCDC_MIRROR(obs_sub);
+#undef SCDC_MIRROR
+  for (int r = 1; r < W; ++r) {
+    CU(cudaSetDevice(hs[r]->device));
+    AllocScope scope(hs[r]->stream);
+    CU(hs[r]->flag.alloc(1));
+  }
+  return SCDC_OK;
+}
 
 }  // namespace
 
@@ -1521,34 +1831,43 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
   if (!res->counts && !res->counts_device) return fail(SCDC_EINVAL, "result.counts and result.counts_device are both NULL");
   if (o->return_distributions && !res->distributions)
     return fail(SCDC_EINVAL, "return_distributions set but result.distributions is NULL");
-  const double t0 = now_ms();
+  const double t0 = now_ms(), h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes;
   memset(&res->stats, 0, sizeof res->stats);
   cudaStream_t s = o->stream ? (cudaStream_t)o->stream : h->stream;
   rc = run_device(h, o, o->return_distributions ? res->distributions : nullptr, &res->stats, s);
   if (rc) return rc;
   const double t1 = now_ms();
   const size_t n = (size_t)h->R * h->ncols;
-  if (res->counts_device && n) {
-    scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->counts.p, (long long*)res->counts_device);
+  const bool f32 = o->precision == SCDC_FP32_FAST;
+  if (n && (res->counts_device || res->band_device)) {
+    if (res->counts_device)
+      scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->counts.p, (long long*)res->counts_device);
+    if (res->band_device) {
+      if (f32) scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->band.p, (long long*)res->band_device);
+      else CU(cudaMemsetAsync(res->band_device, 0, n * sizeof(long long), s));
+    }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     res->stats.kernel_launches += 1;
   }
   if (res->counts) {
-    std::unique_ptr<uint32_t[]> raw32(new uint32_t[n ? n : 1]);
-    if (n) CU(cudaMemcpy(raw32.get(), h->counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    const int n_thr = (n > (1u << 20)) ? 4 : 1;  // widen + NA marks, a few host threads on large tables
-    std::vector<std::thread> th;
-    for (int w = 0; w < n_thr; ++w)
-      th.emplace_back([&, w]() {
-        const size_t lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
-        for (size_t i = lo; i < hi; ++i) res->counts[i] = h->obs_na[i] ? SCDC_COUNT_NA : (uint64_t)raw32[i];
-      });
-    for (auto& t : th) t.join();
+    rc = counts_to_host(h, h->counts.p, res->counts);
+    if (rc) return rc;
+  }
+  if (res->band_counts) {
+    if (f32) {
+      rc = counts_to_host(h, h->band.p, res->band_counts);
+      if (rc) return rc;
+    } else {
+      const std::vector<uint8_t>& na = *h->obs_na;
+      for (size_t i = 0; i < n; ++i) res->band_counts[i] = na[i] ? SCDC_COUNT_NA : 0;
+    }
   }
   res->stats.ms_merge = now_ms() - t1;
   res->stats.ms_total = now_ms() - t0;
   res->stats.n_gpus = 1;
+  res->stats.h2d_bytes = g_h2d_bytes - h2d0;
+  res->stats.d2h_bytes = g_d2h_bytes - d2h0;
   return SCDC_OK;
 }
 
@@ -1589,131 +1908,183 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     pt.lap("perm_counts: create");
     scdc_result r1 = *res;
     r1.counts_device = nullptr;
+    r1.band_device = nullptr;
     rc = scdc_run(h, o, &r1);
     pt.lap("perm_counts: run");
     res->stats = r1.stats;
     res->stats.ms_upload = h->ms_upload;
+    res->stats.h2d_bytes += h->h2d_bytes;
     scdc_release(h);
     pt.lap("perm_counts: release");
     res->stats.ms_total = now_ms() - t0;
     return rc;
   }
-  // ---- multi-GPU: replicate ranges sharded over W devices, one host thread per device ----
-  if (!g_nccl.load()) return fail(SCDC_ENCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  // ---- multi-GPU: replicate ranges sharded over W devices -----------------------------------------------------------
+  // The problem is validated and uploaded ONCE (device ids[0], with the same overlaps as the single-GPU call), broadcast to
+  // the other devices over NVLink (ncclBroadcast; peer copies when NCCL is unavailable), every device runs its replicate
+  // range on its own host thread, and the uint32 counters are merged with one ncclAllReduce (or peer copies + adds).
+  const double h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes, p2p0 = g_p2p_bytes;
+  const bool f32 = o->precision == SCDC_FP32_FAST;
   std::vector<scdc_handle*> hs(W, nullptr);
   std::vector<int> rcs(W, 0);
   std::vector<std::string> errs(W);
   std::vector<scdc_stats> sts(W);
   std::vector<scdc_options> os(W, *o);
   const int64_t per = (o->iterations + W - 1) / W;
+  for (int r = 0; r < W; ++r) {
+    memset(&sts[r], 0, sizeof(scdc_stats));
+    os[r].interrupt = nullptr;  // the callback belongs to the calling thread; the workers watch abort_flag
+    const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
+    os[r].iterations = e - b;
+    os[r].perm_offset = o->perm_offset + b;
+    if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
+    if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
+  }
+  cudaStream_t root_bs = nullptr;  // the root's side of the NCCL broadcast
+  auto cleanup = [&]() {
+    if (root_bs && hs[0]) { cudaSetDevice(hs[0]->device); cudaStreamSynchronize(root_bs); cudaStreamDestroy(root_bs); root_bs = nullptr; }
+    for (auto h : hs) scdc_release(h);
+  };
+  rc = create_impl(p, ids[0], &hs[0], &os[0]);  // W <= iterations / 128: every shard has replicates
+  if (rc) return rc;
+  pt.lap("perm_counts: create on the first device");
+  std::lock_guard<std::mutex> comm_lock(g_nccl_mu);
+  std::vector<int> devs(ids.begin(), ids.begin() + W);
+  const bool use_nccl = nccl_comms_for(devs);
+  {
+    std::vector<Mirror> ms;
+    if (f32) {  // the fp32 copies travel with the rest
+      CU(cudaSetDevice(hs[0]->device));
+      AllocScope scope(hs[0]->stream);
+      rc = ensure_f32_values(hs[0], hs[0]->stream, false);
+      if (!rc && hs[0]->C == 2) rc = ensure_f32_values(hs[0], hs[0]->stream, true);
+      if (!rc && cudaStreamSynchronize(hs[0]->stream) != cudaSuccess) rc = fail(SCDC_ECUDA, "fp32 conversion failed");
+    }
+    if (!rc) rc = clone_handles(hs, devs, ms);
+    if (!rc && use_nccl && cudaSetDevice(hs[0]->device) == cudaSuccess) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&root_bs, cudaStreamNonBlocking, hi) != cudaSuccess) rc = fail(SCDC_ECUDA, "stream creation failed");
+    }
+    if (!rc) rc = broadcast_mirrors(hs, ms, use_nccl, root_bs);
+    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+  }
+  pt.lap("perm_counts: broadcast");
   std::atomic<bool> abort_flag{false};
   std::atomic<int> workers_left{W};
   {
     std::vector<std::thread> th;
-    for (int r = 0; r < W; ++r) {
-      th.emplace_back([&, r]() {
-        struct Done { std::atomic<int>& n; ~Done() { n.fetch_sub(1); } } done_guard{workers_left};
-        memset(&sts[r], 0, sizeof(scdc_stats));
-        os[r].interrupt = nullptr;  // the callback belongs to the calling thread; the workers watch abort_flag
-        const int64_t b = std::min<int64_t>(o->iterations, per * r), e = std::min<int64_t>(o->iterations, per * (r + 1));
-        os[r].iterations = e - b;
-        os[r].perm_offset = o->perm_offset + b;
-        if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
-        if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
-        rcs[r] = create_impl(p, ids[r], &hs[r], os[r].iterations > 0 ? &os[r] : nullptr);
-        if (rcs[r]) { errs[r] = g_err; return; }
+    auto body = [&](int r) {
+      struct Done { std::atomic<int>& n; ~Done() { n.fetch_sub(1); } } done_guard{workers_left};
+      try {
+        const double h2d_before = g_h2d_bytes;
         if (o->interrupt) hs[r]->abort = &abort_flag;
-        if (os[r].iterations > 0) {
-          rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
-          if (rcs[r]) errs[r] = g_err;
-        } else {
-          cudaSetDevice(hs[r]->device);
-          hs[r]->counts.ensure((size_t)hs[r]->R * hs[r]->ncols + 1);
-          cudaMemset(hs[r]->counts.p, 0, ((size_t)hs[r]->R * hs[r]->ncols + 1) * sizeof(uint32_t));
-        }
-      });
+        rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
+        if (rcs[r]) errs[r] = g_err;
+        sts[r].h2d_bytes = g_h2d_bytes - h2d_before;
+      } catch (const std::bad_alloc&) {
+        rcs[r] = SCDC_ENOMEM; errs[r] = "host allocation failed in a device worker";
+      } catch (...) {
+        rcs[r] = SCDC_ECUDA; errs[r] = "unexpected exception in a device worker";
+      }
+    };
+    try {
+      for (int r = 1; r < W; ++r) th.emplace_back(body, r);
+    } catch (...) {  // thread creation failed: the remaining devices run one after the other on this thread
+      for (int r = (int)th.size() + 1; r < W; ++r) body(r);
     }
     if (o->interrupt) {
+      std::thread t0;
+      bool own_thread = true;
+      try { t0 = std::thread(body, 0); } catch (...) { own_thread = false; }
+      if (!own_thread) body(0);
       while (workers_left.load() > 0) {
         if (!abort_flag.load() && o->interrupt(o->interrupt_user) != 0) abort_flag.store(true);
         std::this_thread::sleep_for(std::chrono::milliseconds(20));
       }
+      if (t0.joinable()) t0.join();
+    } else {
+      body(0);
     }
     for (auto& t : th) t.join();
   }
-  auto cleanup = [&]() { for (auto h : hs) scdc_release(h); };
   for (int r = 0; r < W; ++r)
-    if (rcs[r]) { g_err = errs[r]; cleanup(); return rcs[r]; }
+    if (rcs[r]) { cleanup(); g_err = errs[r]; return rcs[r]; }
+  pt.lap("perm_counts: run");
   const double t1 = now_ms();
   const size_t n = (size_t)p->n_rows * hs[0]->ncols;
-  std::vector<DBuf<long long>> wide(W);
-  // communicators are created once per device set and kept for the life of the process (ncclCommInitAll costs ~1.5 s)
-  static std::mutex comm_mu;
-  static std::vector<int> comm_devs;
-  static std::vector<void*> comm_cache;
-  std::lock_guard<std::mutex> comm_lock(comm_mu);
-  std::vector<int> devs(ids.begin(), ids.begin() + W);
-  int nrc = 0;
-  if (comm_devs != devs) {
-    for (void* c : comm_cache) if (c) g_nccl.CommDestroy(c);
-    comm_cache.assign(W, nullptr);
-    comm_devs.clear();
-    nrc = g_nccl.CommInitAll(comm_cache.data(), W, devs.data());
-    if (nrc != 0) {
-      comm_cache.clear();
-      cleanup();
-      return fail(SCDC_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-    }
-    comm_devs = devs;
-  }
-  std::vector<void*>& comms = comm_cache;
+  // total replicates <= 2e9 (validate_options), so the uint32 counters cannot overflow in the sum
   int bad = 0;
-  for (int r = 0; r < W && !bad; ++r) {
-    cudaSetDevice(hs[r]->device);
-    if (wide[r].alloc(n + 1) != cudaSuccess) { bad = 1; break; }
-    if (n) scdc::k_widen_counts<<<(unsigned)((n + 255) / 256), 256, 0, hs[r]->stream>>>(n, hs[r]->counts.p, wide[r].p);
-  }
-  if (!bad && n) {
-    g_nccl.GroupStart();
-    for (int r = 0; r < W; ++r) {
-      nrc = g_nccl.AllReduce(wide[r].p, wide[r].p, n, kNcclInt64, kNcclSum, comms[r], hs[r]->stream);
-      if (nrc != 0) bad = 2;
+  const int n_sets = f32 ? 2 : 1;  // exceedance counters (+ band counters)
+  if (n) {
+    if (use_nccl) {
+      for (int k = 0; k < n_sets && !bad; ++k) {
+        int nrc = g_nccl.GroupStart();
+        for (int r = 0; r < W && nrc == 0; ++r) {
+          uint32_t* buf = k ? hs[r]->band.p : hs[r]->counts.p;
+          nrc = g_nccl.AllReduce(buf, buf, n, kNcclUint32, kNcclSum, g_comms[r], hs[r]->stream);
+        }
+        if (g_nccl.GroupEnd() != 0 || nrc != 0) bad = 2;
+      }
+    } else {
+      // no NCCL: the root pulls every peer's counters over NVLink (cudaMemcpyPeer) and adds them
+      cudaSetDevice(hs[0]->device);
+      AllocScope scope(hs[0]->stream);
+      DBuf<uint32_t> tmp;
+      if (tmp.alloc(n) != cudaSuccess) bad = 1;
+      for (int k = 0; k < n_sets && !bad; ++k) {
+        for (int r = 1; r < W && !bad; ++r) {
+          uint32_t* src = k ? hs[r]->band.p : hs[r]->counts.p;
+          uint32_t* dst = k ? hs[0]->band.p : hs[0]->counts.p;
+          if (cudaMemcpyPeerAsync(tmp.p, hs[0]->device, src, hs[r]->device, n * sizeof(uint32_t), hs[0]->stream) != cudaSuccess) { bad = 3; break; }
+          scdc::k_add_counts<<<(unsigned)((n + 255) / 256), 256, 0, hs[0]->stream>>>(n, tmp.p, dst);
+          g_p2p_bytes += (double)n * sizeof(uint32_t);
+        }
+      }
+      if (!bad && cudaStreamSynchronize(hs[0]->stream) != cudaSuccess) bad = 3;
     }
-    nrc = g_nccl.GroupEnd();
-    if (nrc != 0) bad = 2;
   }
   for (int r = 0; r < W; ++r) {
     cudaSetDevice(hs[r]->device);
     if (cudaStreamSynchronize(hs[r]->stream) != cudaSuccess) bad = bad ? bad : 3;
   }
-  std::vector<long long> raw(n);
-  if (!bad && n) {
+  if (!bad) {
     cudaSetDevice(hs[0]->device);
-    if (cudaMemcpy(raw.data(), wide[0].p, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) bad = 3;
+    if (counts_to_host(hs[0], hs[0]->counts.p, res->counts)) bad = 3;
+    if (!bad && res->band_counts) {
+      if (f32) { if (counts_to_host(hs[0], hs[0]->band.p, res->band_counts)) bad = 3; }
+      else {
+        const std::vector<uint8_t>& na = *hs[0]->obs_na;
+        for (size_t i = 0; i < n; ++i) res->band_counts[i] = na[i] ? SCDC_COUNT_NA : 0;
+      }
+    }
   }
   if (bad) {
-    for (auto& w : wide) { w.release(); }
     cleanup();
     return fail(bad == 1 ? SCDC_ENOMEM : bad == 2 ? SCDC_ENCCL : SCDC_ECUDA, "counter merge across %d GPUs failed (stage %d)", W, bad);
   }
-  finish_counts(hs[0], raw, res->counts);
   for (int r = 0; r < W; ++r) {
     res->stats.ms_labels = std::max(res->stats.ms_labels, sts[r].ms_labels);
     res->stats.ms_reduce = std::max(res->stats.ms_reduce, sts[r].ms_reduce);
     res->stats.ms_score = std::max(res->stats.ms_score, sts[r].ms_score);
     res->stats.ms_device = std::max(res->stats.ms_device, sts[r].ms_device);
-    res->stats.ms_upload = std::max(res->stats.ms_upload, hs[r]->ms_upload);
     res->stats.reduce_bytes += sts[r].reduce_bytes;
     res->stats.reduce_wavefronts += sts[r].reduce_wavefronts;
     res->stats.reduce_launches += sts[r].reduce_launches;
     res->stats.kernel_launches += sts[r].kernel_launches + 1;
     res->stats.batch_size = sts[r].batch_size;
+    res->stats.h2d_bytes += sts[r].h2d_bytes;   // uploaded label slices, counted by each worker thread
   }
-  for (int r = 0; r < W; ++r) { cudaSetDevice(hs[r]->device); wide[r].release(); }
+  res->stats.ms_upload = hs[0]->ms_upload;
+  res->stats.h2d_bytes += hs[0]->h2d_bytes;
+  (void)h2d0;
+  res->stats.d2h_bytes = g_d2h_bytes - d2h0;
+  res->stats.p2p_bytes = g_p2p_bytes - p2p0;
   cleanup();
   res->stats.ms_merge = now_ms() - t1;
   res->stats.ms_total = now_ms() - t0;
   res->stats.n_gpus = W;
+  res->stats.reserved = use_nccl ? 1 : 0;
   return SCDC_OK;
 }
 
@@ -1822,6 +2193,103 @@ int scdc_observed_pass(scdc_handle* h, int64_t n, const int32_t* row_lri, const 
     CU(cudaStreamSynchronize(s));
   }
   CU(cudaStreamSynchronize(s));
+  return SCDC_OK;
+}
+
+}  // extern "C"
+
+// ---- f3: integer-coded template and merge-back (host side of the shim) ----------------------------------------------
+namespace {
+// body(lo, hi) over [0, n) on a few host threads (falls back to the calling thread when none can be created)
+template <typename F>
+void parallel_rows(int64_t n, F&& body) {
+  const int n_thr = (n > (1 << 20)) ? (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+  std::vector<std::thread> th;
+  auto part = [&](int w) { body(n * w / n_thr, n * (w + 1) / n_thr); };
+  try {
+    for (int w = 1; w < n_thr; ++w) th.emplace_back(part, w);
+  } catch (...) {
+    for (int w = (int)th.size() + 1; w < n_thr; ++w) part(w);
+  }
+  part(0);
+  for (auto& t : th) t.join();
+}
+}  // namespace
+
+extern "C" {
+
+int scdc_cci_template(int32_t T, int32_t C, int32_t L, const int32_t* lri_order, int32_t N, const int32_t* ct_code,
+                      const int32_t* cond_code, int32_t* emitter, int32_t* receiver, int32_t* lri_idx,
+                      int32_t* ncells_emitter, int32_t* ncells_receiver) {
+  if (T < 1 || L < 1 || (C != 1 && C != 2) || !lri_order) return fail(SCDC_EINVAL, "bad template dimensions");
+  const int64_t n = (int64_t)T * T * L;
+  if (n > 2147483647LL) return fail(SCDC_EINVAL, "template of %lld rows exceeds R's 32-bit row index", (long long)n);
+  std::vector<uint8_t> seen;
+  try {
+    seen.assign((size_t)L, 0);
+  } catch (const std::bad_alloc&) {
+    return fail(SCDC_ENOMEM, "host allocation failed");
+  }
+  for (int l = 0; l < L; ++l) {
+    if (lri_order[l] < 0 || lri_order[l] >= L || seen[lri_order[l]]) return fail(SCDC_EINVAL, "lri_order is not a permutation of 0..L-1");
+    seen[lri_order[l]] = 1;
+  }
+  std::vector<int32_t> ncell((size_t)C * T, 0);
+  if (ncells_emitter || ncells_receiver) {  // add_cell_number: table(cell_type[, condition])
+    if (N < 1 || !ct_code || (C == 2 && !cond_code)) return fail(SCDC_EINVAL, "cell labels are needed for NCELLS");
+    for (int i = 0; i < N; ++i) {
+      const int t = ct_code[i], c = (C == 2) ? cond_code[i] : 0;
+      if (t < 0 || t >= T || c < 0 || c >= C) return fail(SCDC_EINVAL, "label of cell %d out of range", i);
+      ++ncell[(size_t)c * T + t];
+    }
+  }
+  const int64_t TL = (int64_t)T * L;
+  parallel_rows(n, [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const int e = (int)(i / TL), r = (int)((i / L) % T), l = lri_order[i % L];
+      if (emitter) emitter[i] = e;
+      if (receiver) receiver[i] = r;
+      if (lri_idx) lri_idx[i] = l;
+      for (int c = 0; c < C; ++c) {
+        if (ncells_emitter) ncells_emitter[(size_t)c * n + i] = ncell[(size_t)c * T + e];
+        if (ncells_receiver) ncells_receiver[(size_t)c * n + i] = ncell[(size_t)c * T + r];
+      }
+    }
+  });
+  return SCDC_OK;
+}
+
+int scdc_merge_pvalues(int64_t n_full, int64_t n_tested, const int64_t* tested_rows, int32_t ncols, const uint64_t* counts,
+                       int64_t iterations, int32_t L, int32_t nL, int32_t nR, const int32_t* sub_gene, const int32_t* lri_idx,
+                       double* pvalues) {
+  if (n_full < 0 || n_tested < 0 || n_tested > n_full || ncols < 1 || iterations < 1 || !pvalues ||
+      (n_tested > 0 && (!tested_rows || !counts)))
+    return fail(SCDC_EINVAL, "bad merge arguments");
+  const bool differential = ncols > 1;
+  if (differential && (ncols != 3 + nL + nR || !sub_gene || !lri_idx || L < 1))
+    return fail(SCDC_EINVAL, "differential merge needs ncols = 3 + max_nL + max_nR, sub_gene and lri_idx");
+  for (int64_t k = 0; k < n_tested; ++k)
+    if (tested_rows[k] < 0 || tested_rows[k] >= n_full) return fail(SCDC_EINVAL, "tested_rows[%lld] out of range", (long long)k);
+  const double nan = std::nan(""), it = (double)iterations;
+  const int nS = nL + nR;
+  parallel_rows(n_full, [&](int64_t lo, int64_t hi) {  // rows outside the tested subset: 1 (:434-441); absent subunits: NA (:442-469)
+    for (int c = 0; c < ncols; ++c) {
+      double* col = pvalues + (size_t)c * n_full;
+      if (!differential || c < 3) {
+        for (int64_t i = lo; i < hi; ++i) col[i] = 1.0;
+      } else {
+        const int sidx = c - 3;
+        for (int64_t i = lo; i < hi; ++i) col[i] = (sub_gene[(size_t)lri_idx[i] * nS + sidx] < 0) ? nan : 1.0;
+      }
+    }
+  });
+  parallel_rows(n_tested, [&](int64_t lo, int64_t hi) {  // p = counts / iterations (:215-259), NA where the count is NA
+    for (int c = 0; c < ncols; ++c) {
+      double* col = pvalues + (size_t)c * n_full;
+      const uint64_t* cnt = counts + (size_t)c * n_tested;
+      for (int64_t k = lo; k < hi; ++k) col[tested_rows[k]] = (cnt[k] == SCDC_COUNT_NA) ? nan : (double)cnt[k] / it;
+    }
+  });
   return SCDC_OK;
 }
 

@@ -842,129 +842,27 @@ __global__ void k_check_uploaded(int N, int T, int C, const uint8_t* __restrict_
 
 // ------------------------------------------------------------------------------------------------------------------
 // staging helper: a warp loads 32 consecutive (cell, value) entries coalesced and re-reads them one by one as a
-// 16-byte broadcast from shared memory (1 wavefront per entry instead of 3 shuffles).
+// broadcast from shared memory (fp64 values: one 16-byte LDS.128 = 2 wavefronts; fp32 values: one 8-byte LDS.64 = 1
+// wavefront, instead of 3 shuffles). VT = double (SCDC_FP64_EXACT) or float (SCDC_FP32_FAST).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 pack_entry(int cell, double v) {
-  long long b = __double_as_longlong(v);
-  return make_uint4((uint32_t)cell, 0u, (uint32_t)b, (uint32_t)(b >> 32));
-}
-__device__ __forceinline__ double entry_value(const uint4& e) {
-  return __longlong_as_double((long long)(((unsigned long long)e.w << 32) | e.z));
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// K2a: differential pass 1. Cell types are fixed, only the condition bit varies per replicate, so the entries of a
-// gene column, pre-sorted by (cell type, cell) [stable: ascending cell order inside every (cell type, cond') group is
-// kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 128 replicates
-// (4 per lane): one uniform 16-byte load brings the condition bits of a cell for all 128.
-// M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
-// grid.x = nGa * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
-// ------------------------------------------------------------------------------------------------------------------
-// acc1 += v if sel != 0 else acc0 += v, written as two fused multiply-adds with a 1.0 / 0.0 selector: v * 1.0 + acc is
-// exactly acc + v (the product is exact, one rounding) and v * 0.0 + acc leaves acc unchanged, so the result is bit-identical
-// to the branchy form, in 5 instructions instead of the 7 (two adds + four selects + test) the compiler emits for it.
-__device__ __forceinline__ void sel_add(double& acc1, double& acc0, uint32_t sel, double v) {
-  // (two predicated add.f64 in inline PTX do not survive either: ptxas turns them into add + FSEL pairs)
-  const int hi1 = sel ? 0x3FF00000 : 0;
-  const double b1 = __hiloint2double(hi1, 0), b0 = __hiloint2double(hi1 ^ 0x3FF00000, 0);
-  acc1 = fma(v, b1, acc1);
-  acc0 = fma(v, b0, acc0);
-}
-
-template <int U>
-__global__ void __launch_bounds__(256) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
-                                                    const int* __restrict__ rowidx_s, const double* __restrict__ values_s,
-                                                    const uint32_t* __restrict__ bits1, int Bw,
-                                                    const double* __restrict__ ngroup, const int* __restrict__ gene_order,
-                                                    double* __restrict__ M1) {
-  __shared__ uint4 stage_all[8][64];  // per warp: two buffers of 32 entries
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-  const long long task = (long long)blockIdx.x * W + warp;
-  if (task >= (long long)nGa * nWC) return;  // nGa active genes (gene_order), G = layout stride of M1
-  const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
-  uint4* stage = stage_all[warp];
-  const int K = 2 * T;
-  const uint32_t lane_bit = 1u << lane;
-  const int* sp = segptr + (size_t)g * (T + 1);
-  const char* bitbase = reinterpret_cast<const char*>(bits1 + wc * 4);  // + cell * Bw * 4 bytes: this warp's 128 condition bits
-  asm("" : "+l"(bitbase));
-  const uint32_t ubw = (uint32_t)Bw * 4u;  // byte stride: the address is one IMAD.WIDE (u32 cell x u32 stride + 64-bit base)
-  // Same software pipeline as k_scatter: the entries two stages ahead are in flight from global memory, and the condition
-  // bits of the NEXT group of U entries (one uniform 16-byte load per entry, L2 latency) are loaded while the CURRENT
-  // group is accumulated. Padding entries are (cell 0, +0.0): bit-neutral.
-  for (int t = 0; t < T; ++t) {
-    const int beg = sp[t], end = sp[t + 1];
-    const int nst = (end - beg + 31) >> 5;
-    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-    if (nst > 0) {
-      int cell_n = 0;
-      double v_n = 0.0;
-      if (beg + lane < end) { cell_n = __ldcs(rowidx_s + beg + lane); v_n = __ldcs(values_s + beg + lane); }
-      __syncwarp();  // every lane is done with the previous segment's buffers
-      stage[lane] = pack_entry(cell_n, v_n);
-      cell_n = 0; v_n = 0.0;
-      if (beg + 32 + lane < end) { cell_n = __ldcs(rowidx_s + beg + 32 + lane); v_n = __ldcs(values_s + beg + 32 + lane); }
-      __syncwarp();
-      double valN[U];
-      uint4 bN[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint4 en = stage[u];
-        valN[u] = entry_value(en);
-        bN[u] = __ldg(reinterpret_cast<const uint4*>(bitbase + (uint64_t)en.x * ubw));
-      }
-      for (int s = 0; s < nst; ++s) {
-        uint4* cur_buf = stage + (s & 1) * 32;
-        uint4* nxt_buf = stage + ((s + 1) & 1) * 32;
-        __syncwarp();
-        nxt_buf[lane] = pack_entry(cell_n, v_n);
-        {
-          const int e = beg + (s + 2) * 32 + lane;
-          cell_n = 0; v_n = 0.0;
-          if (e < end) { cell_n = __ldcs(rowidx_s + e); v_n = __ldcs(values_s + e); }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int gq = 0; gq < 32 / U; ++gq) {
-          double val[U];
-          uint4 b[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) { val[u] = valN[u]; b[u] = bN[u]; }
-          const uint4* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint4 en = src[u];
-            valN[u] = entry_value(en);
-            bN[u] = __ldg(reinterpret_cast<const uint4*>(bitbase + (uint64_t)en.x * ubw));
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            sel_add(a1[0], a0[0], b[u].x & lane_bit, val[u]);
-            sel_add(a1[1], a0[1], b[u].y & lane_bit, val[u]);
-            sel_add(a1[2], a0[2], b[u].z & lane_bit, val[u]);
-            sel_add(a1[3], a0[3], b[u].w & lane_bit, val[u]);
-          }
-        }
-      }
-    }
-    const double n0 = ngroup[t], n1 = ngroup[T + t];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      size_t base = (((size_t)(wc * 4 + j) * G + g) * K) * 32 + lane;
-      __stcs(&M1[base + (size_t)t * 32], a0[j] / n0);
-      __stcs(&M1[base + (size_t)(T + t) * 32], a1[j] / n1);
-    }
+template <typename VT> struct Ent;
+template <> struct Ent<double> {
+  typedef uint4 pack;
+  static __device__ __forceinline__ pack make(int cell, double v) {
+    long long b = __double_as_longlong(v);
+    return make_uint4((uint32_t)cell, 0u, (uint32_t)b, (uint32_t)(b >> 32));
   }
-}
+  static __device__ __forceinline__ double value(const pack& e) {
+    return __longlong_as_double((long long)(((unsigned long long)e.w << 32) | e.z));
+  }
+};
+template <> struct Ent<float> {
+  typedef uint2 pack;
+  static __device__ __forceinline__ pack make(int cell, float v) { return make_uint2((uint32_t)cell, __float_as_uint(v)); }
+  static __device__ __forceinline__ float value(const pack& e) { return __uint_as_float(e.y); }
+};
 
-// ------------------------------------------------------------------------------------------------------------------
-// K2b: general segmented sum. One warp = one gene column x (32*J) replicates; lane owns J replicates and walks the
-// column in ascending cell order doing acc[label][j][lane] += x in shared memory (fp64). The accumulator row stride
-// is a multiple of 32 banks and the column index is the lane, so the read-modify-write is conflict-free and needs no
-// atomics whatever the labels are. lab2 layout: [cell][Bpad] bytes, lane's J labels adjacent (one J-byte load).
-// M2 layout: [chunk32][gene][k][32 lanes], value = sum / n_k.
-// grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K*J*32*8 + 1024).
-// ------------------------------------------------------------------------------------------------------------------
+// label bytes of one lane (k_scatter: J group codes; k_pass1_cond: the byte with its 8 condition bits)
 template <int J> struct LabWord;
 template <> struct LabWord<1> { typedef uint32_t type; };  // one label byte, zero-extended by the load itself
 template <> struct LabWord<2> { typedef uint16_t type; };
@@ -993,65 +891,277 @@ __device__ __forceinline__ uint32_t load_labels<4>(const uint8_t* p) {
   return r;
 }
 
-template <int J, int U, bool PAIR>
+// ------------------------------------------------------------------------------------------------------------------
+// Pass-1 copy of the matrix, built ON THE DEVICE (replaces a host counting sort + a second H2D of the matrix): inside
+// every gene column the entries are stably sorted by the ORIGINAL cell type of their cell, so that ascending cell order
+// inside every (cell type, cond') group is kept and the pass-1 sums stay bit-identical to the reference's sequential sum.
+// One warp per gene column: histogram of the column's cell types (shared memory), exclusive scan -> segptr[g][0..T],
+// then a second sweep in column order, 32 entries at a time: lanes with the same cell type are ranked by lane id
+// (__match_any_sync), so equal keys keep their order. The copy is written as 16-byte (cell, value) records, the unit the
+// pass-1 kernel fetches with one load. grid = ceil(G / W), block = 32 * W, smem = W * (T + 1) * 4.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sort_by_celltype(int G, int T, const int* __restrict__ colptr,
+                                                          const int* __restrict__ rowidx, const double* __restrict__ values,
+                                                          const uint8_t* __restrict__ ct, const int* __restrict__ gene_order,
+                                                          int* __restrict__ segptr, uint4* __restrict__ rec_s) {
+  extern __shared__ int sm_sort[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int gi = blockIdx.x * W + warp;
+  if (gi >= G) return;
+  const int g = gene_order ? gene_order[gi] : gi;   // heavy columns first when an order is given
+  int* cur = sm_sort + warp * (T + 1);
+  for (int t = lane; t <= T; t += 32) cur[t] = 0;
+  __syncwarp();
+  const int beg = colptr[g], end = colptr[g + 1];
+  for (int e = beg + lane; e < end; e += 32) atomicAdd(&cur[ct[rowidx[e]]], 1);
+  __syncwarp();
+  {  // exclusive scan of cur[0..T): lane owns ceil(T / 32) consecutive labels
+    const int per = (T + 31) / 32, t0 = lane * per;
+    int loc = 0;
+    for (int k = 0; k < per; ++k) loc += (t0 + k < T) ? cur[t0 + k] : 0;
+    int inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    int run = beg + inc - loc;
+    __syncwarp();
+    for (int k = 0; k < per; ++k) {
+      if (t0 + k < T) {
+        const int c = cur[t0 + k];
+        cur[t0 + k] = run;
+        segptr[(size_t)g * (T + 1) + t0 + k] = run;
+        run += c;
+      }
+    }
+    if (lane == 31) segptr[(size_t)g * (T + 1) + T] = end;
+  }
+  __syncwarp();
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const bool valid = e < end;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const int cell = rowidx[e];
+      const double v = values[e];
+      const int t = ct[cell];
+      const unsigned same = __match_any_sync(act, t);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      const int dst = cur[t] + rank;
+      __syncwarp(act);
+      if (rank == 0) cur[t] += __popc(same);
+      rec_s[dst] = Ent<double>::make(cell, v);
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 copies of the matrix values (SCDC_FP32_FAST): round-to-nearest of every fp64 value
+__global__ void k_to_float(size_t n, const double* __restrict__ in, float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+// ... and of the pass-1 records: (cell, fp64) 16 bytes -> (cell, fp32) 8 bytes
+__global__ void k_rec_to_float(size_t n, const uint4* __restrict__ in, uint2* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint4 e = in[i];
+    out[i] = Ent<float>::make((int)e.x, (float)Ent<double>::value(e));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2a: differential pass 1. Cell types are fixed, only the condition bit varies per replicate, so the entries of a
+// gene column, pre-sorted by (cell type, cell) [stable: ascending cell order inside every (cell type, cond') group is
+// kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 128 replicates
+// (4 per lane): one uniform 16-byte load brings the condition bits of a cell for all 128.
+// M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
+// grid.x = nGa * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
+// ------------------------------------------------------------------------------------------------------------------
+// acc1 += v if sel != 0 else acc0 += v, written as two fused multiply-adds with a 1.0 / 0.0 selector: v * 1.0 + acc is
+// exactly acc + v (the product is exact, one rounding) and v * 0.0 + acc leaves acc unchanged, so the result is bit-identical
+// to the branchy form, in 5 instructions instead of the 7 (two adds + four selects + test) the compiler emits for it.
+__device__ __forceinline__ void sel_add(double& acc1, double& acc0, uint32_t sel, double v) {
+  // (two predicated add.f64 in inline PTX do not survive either: ptxas turns them into add + FSEL pairs)
+  const int hi1 = sel ? 0x3FF00000 : 0;
+  const double b1 = __hiloint2double(hi1, 0), b0 = __hiloint2double(hi1 ^ 0x3FF00000, 0);
+  acc1 = fma(v, b1, acc1);
+  acc0 = fma(v, b0, acc0);
+}
+__device__ __forceinline__ void sel_add(float& acc1, float& acc0, uint32_t sel, float v) {
+  const int w1 = sel ? 0x3F800000 : 0;
+  acc1 = fmaf(v, __int_as_float(w1), acc1);
+  acc0 = fmaf(v, __int_as_float(w1 ^ 0x3F800000), acc0);
+}
+
+// Pass-1 condition bits, re-packed in place for k_pass1_cond. The label generators write, per cell, one 32-bit word per
+// 32 replicates (bit = lane). The pass-1 kernel gives every lane 8 replicates (q = 256 wc + 32 j + lane, j = 0..7) and
+// wants THEIR 8 bits in one byte, so that a warp fetches the bits of a cell with one 32-byte request (one sector, one cycle
+// of register write-back) instead of broadcasting 16 or 32 bytes to all 32 lanes. One thread per (cell, 256-replicate group):
+// 8 words in, the same 32 bytes out: byte `lane`, bit j = bit `lane` of word j. n_groups = N * B / 256 over the whole buffer.
+__global__ void k_bits_transpose8(size_t n_groups, uint32_t* __restrict__ bits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_groups) return;
+  uint4* p = reinterpret_cast<uint4*>(bits + i * 8);
+  const uint4 lo = p[0], hi = p[1];
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t out[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int lane = 4 * m + b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o |= ((w[j] >> lane) & 1u) << (8 * b + j);
+    }
+    out[m] = o;
+  }
+  p[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  p[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+// No shared memory and no warp synchronisation. A warp covers 256 replicates (8 per lane, 16 register accumulators):
+// every lane fetches the entry's 16-byte (fp32: 8-byte) record itself with a warp-uniform load and the byte that holds its
+// own 8 condition bits of the entry's cell (k_bits_transpose8): 5 cycles of load-store-unit write-back per entry x 256
+// replicates (fp32: 3), where round 1's layout paid 8 per entry x 128. That matters because the load-store pipe is what the
+// pass-2 scatter saturates, and this kernel is meant to run NEXT TO it (k_scatter holds nearly all of an SM's shared
+// memory at K > 100 but few registers and issue slots; this kernel needs only registers, FP64 and issue slots).
+// The loads are software-pipelined three groups deep (records of group i + 2 and bits of group i + 1 in flight while
+// group i is accumulated). Padding records are (cell 0, +0.0): bit-neutral.
+// bits: [cell][Bb] bytes with Bb = B / 8 (one batch block). grid.x = ceil(nGa * (B / 256) / W), block = 32 * W.
+template <typename VT, int U>
+__global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
+                                                    const typename Ent<VT>::pack* __restrict__ rec,
+                                                    const uint8_t* __restrict__ bits, int Bb,
+                                                    const double* __restrict__ ngroup, const int* __restrict__ gene_order,
+                                                    VT* __restrict__ M1) {
+  typedef typename Ent<VT>::pack pack_t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const long long task = (long long)blockIdx.x * W + warp;
+  if (task >= (long long)nGa * nWC) return;  // nGa active genes (gene_order), G = layout stride of M1
+  const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
+  const int K = 2 * T;
+  const int* sp = segptr + (size_t)g * (T + 1);
+  const uint8_t* bitbase = bits + wc * 32 + lane;  // + cell * Bb: the byte with this lane's 8 condition bits
+  asm("" : "+l"(bitbase));
+  const uint32_t ubb = (uint32_t)Bb;  // the address is one IMAD.WIDE (u32 cell x u32 stride + 64-bit lane base)
+  const pack_t zero = Ent<VT>::make(0, (VT)0);
+  for (int t = 0; t < T; ++t) {
+    const int beg = sp[t], end = sp[t + 1];
+    VT a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = 0; a1[j] = 0; }
+    if (end > beg) {
+      pack_t R0[U], R1[U], R2[U];
+      uint32_t B0[U], B1[U], B2[U];
+      auto load_recs = [&](pack_t (&R)[U], int e0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) R[u] = (e0 + u < end) ? __ldg(rec + e0 + u) : zero;
+      };
+      auto load_bits = [&](uint32_t (&B)[U], const pack_t (&R)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) B[u] = load_labels<1>(bitbase + (uint64_t)R[u].x * ubb);
+      };
+      auto accumulate = [&](const pack_t (&R)[U], const uint32_t (&B)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const VT v = Ent<VT>::value(R[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sel_add(a1[j], a0[j], B[u] & (1u << j), v);
+        }
+      };
+      load_recs(R0, beg);
+      load_bits(B0, R0);
+      load_recs(R1, beg + U);
+      for (int base = beg; base < end; base += 3 * U) {
+        load_bits(B1, R1); load_recs(R2, base + 2 * U); accumulate(R0, B0);
+        load_bits(B2, R2); load_recs(R0, base + 3 * U); accumulate(R1, B1);   // past the end: zero records, bit-neutral
+        load_bits(B0, R0); load_recs(R1, base + 4 * U); accumulate(R2, B2);
+      }
+    }
+    const VT n0 = (VT)ngroup[t], n1 = (VT)ngroup[T + t];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      size_t base = (((size_t)(wc * 8 + j) * G + g) * K) * 32 + lane;
+      __stcs(&M1[base + (size_t)t * 32], a0[j] / n0);
+      __stcs(&M1[base + (size_t)(T + t) * 32], a1[j] / n1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2b: general segmented sum. One warp = one gene column x (32*J) replicates; lane owns J replicates and walks the
+// column in ascending cell order doing acc[label][j][lane] += x in shared memory (VT = fp64, or fp32 in SCDC_FP32_FAST).
+// The accumulator row stride is a multiple of 32 banks and the column index is the lane, so the read-modify-write is
+// conflict-free and needs no atomics whatever the labels are. lab2 layout: [cell][Bpad] bytes, lane's J labels adjacent
+// (one J-byte load). M2 layout: [chunk32][gene][k][32 lanes], value = sum / n_k.
+// grid = (G, ceil(nCJ / W)), block = 32 * W, dynamic smem = W * (K * J * 32 * sizeof(VT) + 64 * sizeof(entry)).
+// Shared-memory wavefronts per (entry x 32 J replicates): fp64 2 (LDS.128 entry broadcast) + 4 J (LDS.64 + STS.64);
+// fp32 1 (LDS.64 broadcast) + 2 J (LDS.32 + STS.32): half the traffic through the pipe that bounds the kernel.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename VT, int J, int U, bool PAIR>
 __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
-                          const double* __restrict__ values, const uint8_t* __restrict__ lab2, int lab_stride,
-                          const double* __restrict__ ngroup, const int* __restrict__ gene_order, double* __restrict__ M2) {
+                          const VT* __restrict__ values, const uint8_t* __restrict__ lab2, int lab_stride,
+                          const double* __restrict__ ngroup, const int* __restrict__ gene_order, VT* __restrict__ M2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef typename LabWord<J>::type lab_t;
+  typedef typename Ent<VT>::pack pack_t;
+  constexpr uint32_t ROW = 32 * sizeof(VT);  // bytes of one accumulator row (32 lanes)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   const int cJ = blockIdx.y * W + warp;
   if (cJ >= nCJ) return;
   const int g = gene_order[blockIdx.x];
-  uint4* stage = reinterpret_cast<uint4*>(smem_raw) + warp * 64;  // two buffers of 32 entries
-  double* acc = reinterpret_cast<double*>(smem_raw + (size_t)W * 1024) + (size_t)warp * K * J * 32 + lane;
-  for (int i = 0; i < K * J; ++i) acc[i * 32] = 0.0;
+  pack_t* stage = reinterpret_cast<pack_t*>(smem_raw) + warp * 64;  // two buffers of 32 entries
+  VT* acc = reinterpret_cast<VT*>(smem_raw + (size_t)W * 64 * sizeof(pack_t)) + (size_t)warp * K * J * 32 + lane;
+  for (int i = 0; i < K * J; ++i) acc[i * 32] = 0;
   const int beg = colptr[g], end = colptr[g + 1];
   const int nst = (end - beg + 31) >> 5;
   const uint8_t* labbase = lab2 + (size_t)cJ * 32 * J + lane * J;
   asm("" : "+l"(labbase));  // one opaque 64-bit value: keeps ptxas from re-adding the uniform base on every label load
   const uint32_t ustride = (uint32_t)lab_stride;  // label address = 64-bit lane base + u32 cell * u32 stride: one IMAD.WIDE
-  char* const accb = reinterpret_cast<char*>(acc);  // J = 1: accumulator row of label l starts at byte l * 256
+  char* const accb = reinterpret_cast<char*>(acc);  // J = 1: accumulator row of label l starts at byte l * ROW
   // Matrix entries and the flushed means are streamed (evict-first) so that they do not push the labels out of L2.
   // The labels of the NEXT group of U entries are loaded (L2 latency) while the CURRENT group is accumulated, and the
   // entries two stages ahead are in flight from global memory: the read-modify-write chain never waits on a load.
   int cell_n = 0;
-  double v_n = 0.0;
+  VT v_n = 0;
   if (beg + lane < end) { cell_n = __ldcs(rowidx + beg + lane); v_n = __ldcs(values + beg + lane); }
-  stage[lane] = pack_entry(cell_n, v_n);
-  cell_n = 0; v_n = 0.0;  // padding entries add +0.0 to cell 0's group: bit-neutral
+  stage[lane] = Ent<VT>::make(cell_n, v_n);
+  cell_n = 0; v_n = 0;  // padding entries add +0.0 to cell 0's group: bit-neutral
   if (beg + 32 + lane < end) { cell_n = __ldcs(rowidx + beg + 32 + lane); v_n = __ldcs(values + beg + 32 + lane); }
   __syncwarp();
-  double valN[U];
+  VT valN[U];
   lab_t lbN[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const uint4 en = stage[u];
-    valN[u] = entry_value(en);
+    const pack_t en = stage[u];
+    valN[u] = Ent<VT>::value(en);
     lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
   }
   for (int s = 0; s < nst; ++s) {
-    uint4* cur_buf = stage + (s & 1) * 32;
-    uint4* nxt_buf = stage + ((s + 1) & 1) * 32;
+    pack_t* cur_buf = stage + (s & 1) * 32;
+    pack_t* nxt_buf = stage + ((s + 1) & 1) * 32;
     __syncwarp();  // every lane is done reading stage s-1 from nxt_buf
-    nxt_buf[lane] = pack_entry(cell_n, v_n);
+    nxt_buf[lane] = Ent<VT>::make(cell_n, v_n);
     {
       const int e = beg + (s + 2) * 32 + lane;
-      cell_n = 0; v_n = 0.0;
+      cell_n = 0; v_n = 0;
       if (e < end) { cell_n = __ldcs(rowidx + e); v_n = __ldcs(values + e); }
     }
     __syncwarp();
 #pragma unroll
     for (int gq = 0; gq < 32 / U; ++gq) {
-      double val[U];
+      VT val[U];
       lab_t lb[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) { val[u] = valN[u]; lb[u] = lbN[u]; }
-      const uint4* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
+      const pack_t* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint4 en = src[u];
-        valN[u] = entry_value(en);
+        const pack_t en = src[u];
+        valN[u] = Ent<VT>::value(en);
         lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
       }
       if (PAIR && J == 1) {
@@ -1061,11 +1171,11 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
         // groups of four were measured no faster).
 #pragma unroll
         for (int u = 0; u < U; u += 2) {
-          double* const p1 = reinterpret_cast<double*>(accb + (lb[u] << 8));
-          double* const p2 = reinterpret_cast<double*>(accb + (lb[u + 1] << 8));
-          const double a1 = *p1, a2 = *p2;
-          const double r1 = a1 + val[u];
-          const double r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
+          VT* const p1 = reinterpret_cast<VT*>(accb + lb[u] * ROW);
+          VT* const p2 = reinterpret_cast<VT*>(accb + lb[u + 1] * ROW);
+          const VT a1 = *p1, a2 = *p2;
+          const VT r1 = a1 + val[u];
+          const VT r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
           *p1 = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
           *p2 = r2;
         }
@@ -1073,16 +1183,16 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (J == 1) {
-            double* const p1 = reinterpret_cast<double*>(accb + (lb[u] << 8));
+            VT* const p1 = reinterpret_cast<VT*>(accb + lb[u] * ROW);
             *p1 = *p1 + val[u];
           } else {
-            // row (label, j) starts at byte (label * J + j) * 256: one byte extract (PRMT) + one multiply-add per row,
-            // the j * 256 part folds into the LDS / STS immediate
-            double* row[J];
-            double cur[J];
+            // row (label, j) starts at byte (label * J + j) * ROW: one byte extract (PRMT) + one multiply-add per row,
+            // the j * ROW part folds into the LDS / STS immediate
+            VT* row[J];
+            VT cur[J];
 #pragma unroll
             for (int j = 0; j < J; ++j)
-              row[j] = reinterpret_cast<double*>(accb + __byte_perm((uint32_t)lb[u], 0u, 0x4440u + j) * (J * 256u) + j * 256);
+              row[j] = reinterpret_cast<VT*>(accb + __byte_perm((uint32_t)lb[u], 0u, 0x4440u + j) * (J * ROW) + j * ROW);
 #pragma unroll
             for (int j = 0; j < J; ++j) cur[j] = *row[j];
 #pragma unroll
@@ -1094,7 +1204,7 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   }
   __syncwarp();
   for (int k = 0; k < K; ++k) {
-    const double nk = ngroup[k];
+    const VT nk = (VT)ngroup[k];
 #pragma unroll
     for (int j = 0; j < J; ++j)
       __stcs(&M2[(((size_t)(cJ * J + j) * G + g) * K + k) * 32 + lane], acc[(k * J + j) * 32] / nk);
@@ -1118,9 +1228,11 @@ struct ScoreArgs {
   const int* row_emit;
   const int* row_recv;
   const double* obs;     // column-major [R][ncols]
-  const double* M1;      // pass-1 means (differential) or nullptr
-  const double* M2;      // pass-2 means / detection means
+  const void* M1;        // pass-1 means (differential) or nullptr; element type MT
+  const void* M2;        // pass-2 means / detection means
   uint32_t* counts;      // column-major [R][ncols]
+  uint32_t* band;        // BAND: comparisons inside the tolerance band, same shape
+  double rel_tol;        // BAND
   double* dist;          // nullptr or [n_valid][ncols_d][R] (this batch's slice)
 };
 
@@ -1128,12 +1240,29 @@ __device__ __forceinline__ double score_of(double a, double b, int score_type) {
   return score_type == 0 ? sqrt(a * b) : (a + b) / 2;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tolerance band of SCDC_FP32_FAST (include/scdc.h, scdc_options.rel_tol). The same fp64 expressions are evaluated by
+// every score kernel, so band membership does not depend on which kernel counted a comparison.
+//   one-sided geometric score, compared as a product x against observed o:  |x - o^2| <= (2 rel_tol) o^2
+//   one-sided arithmetic score s:                                           |s - o|   <= rel_tol |o|
+//   two-sided difference a - b of two non-negative magnitudes:              ||a - b| - |o|| <= rel_tol (a + b)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool band_product(double x, double o2, double rel_tol) { return fabs(x - o2) <= (2.0 * rel_tol) * o2; }
+__device__ __forceinline__ bool band_value(double s, double o, double rel_tol) { return fabs(s - o) <= rel_tol * fabs(o); }
+__device__ __forceinline__ bool band_diff(double a, double b, double abs_o, double rel_tol) {
+  return fabs(fabs(a - b) - abs_o) <= rel_tol * (a + b);
+}
+
+template <typename MT, bool BAND>
 __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
+  const MT* const M1 = reinterpret_cast<const MT*>(A.M1);
+  const MT* const M2 = reinterpret_cast<const MT*>(A.M2);
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int K = A.C * A.T, nS = A.nL + A.nR;
   const int ncols_d = (A.C == 2) ? 3 : 1;
+  const double rt = A.rel_tol;
   for (int row = warp_global; row < A.R; row += n_warps) {
     const int l = A.row_lri[row], e = A.row_emit[row], r = A.row_recv[row];
     int gs[8];
@@ -1142,9 +1271,11 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
     double ob[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) ob[c] = (c < A.ncols) ? A.obs[(size_t)c * A.R + row] : 0.0;
-    uint32_t cnt[16];
+    uint32_t cnt[16], bnd[BAND ? 16 : 1];
 #pragma unroll
     for (int c = 0; c < 16; ++c) cnt[c] = 0;
+#pragma unroll
+    for (int c = 0; c < (BAND ? 16 : 1); ++c) bnd[c] = 0;
     for (int ch = 0; ch < A.nChunks; ++ch) {
       const bool valid = (ch * 32 + lane) < A.n_valid;
       const size_t cb = (size_t)ch * A.G;
@@ -1155,19 +1286,23 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
         for (int s = 0; s < 8; ++s) {
           if (s < nS && gs[s] >= 0) {
             const bool isL = s < A.nL;
-            double v = A.M2[((cb + gs[s]) * K + (isL ? e : r)) * 32 + lane];
+            double v = (double)M2[((cb + gs[s]) * K + (isL ? e : r)) * 32 + lane];
             if (isL) { mL = hL ? fmin(mL, v) : v; hL = true; } else { mR = hR ? fmin(mR, v) : v; hR = true; }
           }
         }
         double sc = score_of(mL, mR, A.score_type);
         uint32_t b = __ballot_sync(0xffffffffu, valid && (sc >= ob[0]));
         cnt[0] += __popc(b);
+        if (BAND) {
+          const bool in = A.score_type == 0 ? band_product(mL * mR, ob[0] * ob[0], rt) : band_value(sc, ob[0], rt);
+          bnd[0] += __popc(__ballot_sync(0xffffffffu, valid && in));
+        }
         if (A.dist && valid) A.dist[((size_t)(ch * 32 + lane) * ncols_d) * A.R + row] = sc;
       } else {
-        double s1[2], s2[2];
-        double dsub[8];
+        double s1[2], s2[2], x2[2];
+        double dsub[8], ssub[8];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) dsub[s] = 0.0;
+        for (int s = 0; s < 8; ++s) { dsub[s] = 0.0; ssub[s] = 0.0; }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           double mL = 0.0, mR = 0.0, qL = 0.0, qR = 0.0;
@@ -1177,7 +1312,8 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
             if (s < nS && gs[s] >= 0) {
               const bool isL = s < A.nL;
               const size_t idx = ((cb + gs[s]) * K + c * A.T + (isL ? e : r)) * 32 + lane;
-              double v1 = A.M1[idx], v2 = A.M2[idx];
+              double v1 = (double)M1[idx], v2 = (double)M2[idx];
+              ssub[s] = (c == 0) ? v1 : (v1 + dsub[s]);    // cond2 + cond1: the scale of the band (dsub still holds cond1)
               dsub[s] = (c == 0) ? v1 : (v1 - dsub[s]);  // cond2 - cond1 (R/utils_cci.R:212-239)
               if (isL) {
                 mL = hL ? fmin(mL, v1) : v1; qL = hL ? fmin(qL, v2) : v2; hL = true;
@@ -1188,6 +1324,7 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
           }
           s1[c] = score_of(mL, mR, A.score_type);
           s2[c] = score_of(qL, qR, A.score_type);
+          x2[c] = qL * qR;
         }
         const double de = s1[1] - s1[0];
         cnt[0] += __popc(__ballot_sync(0xffffffffu, valid && (fabs(de) >= fabs(ob[0]))));
@@ -1196,6 +1333,22 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
           if (s < nS) cnt[3 + s] += __popc(__ballot_sync(0xffffffffu, valid && gs[s] >= 0 && (fabs(dsub[s]) >= fabs(ob[3 + s]))));
+        }
+        if (BAND) {
+          bnd[0] += __popc(__ballot_sync(0xffffffffu, valid && band_diff(s1[1], s1[0], fabs(ob[0]), rt)));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const bool in = A.score_type == 0 ? band_product(x2[c], ob[1 + c] * ob[1 + c], rt) : band_value(s2[c], ob[1 + c], rt);
+            bnd[1 + c] += __popc(__ballot_sync(0xffffffffu, valid && in));
+          }
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < nS) {
+              // band_diff(cond2, cond1) with the difference and the sum already formed
+              const bool in = fabs(fabs(dsub[s]) - fabs(ob[3 + s])) <= rt * ssub[s];
+              bnd[3 + s] += __popc(__ballot_sync(0xffffffffu, valid && gs[s] >= 0 && in));
+            }
+          }
         }
         if (A.dist && valid) {
           double* d = A.dist + ((size_t)(ch * 32 + lane) * 3) * A.R + row;
@@ -1208,7 +1361,10 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        if (c < A.ncols) A.counts[(size_t)c * A.R + row] += cnt[c];
+        if (c < A.ncols) {
+          A.counts[(size_t)c * A.R + row] += cnt[c];
+          if (BAND) A.band[(size_t)c * A.R + row] += bnd[BAND ? c : 0];
+        }
     }
   }
 }
@@ -1227,9 +1383,11 @@ __global__ void __launch_bounds__(256) k_score_count(ScoreArgs A) {
 // (sqrt(a*b) >= observed) == (a*b >= thr) exactly and the fp64 sqrt disappears.
 // k_score_det: detection mode (one column). k_score_diff (below): differential mode (3 + nL + nR columns).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
+template <typename MT>
+__device__ __forceinline__ void cp_async_elem(MT* smem_dst, const MT* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+  if (sizeof(MT) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -1248,19 +1406,24 @@ struct ScoreDetArgs {
   const int* row_recv;
   const double* obs;    // [R] observed CCI_SCORE, original row ids
   const double* thr;    // [R] product thresholds (geometric score)
-  const double* M2;     // group means [chunk32][gene][T][32]
+  const void* M2;       // group means [chunk32][gene][T][32], element type MT
   uint32_t* counts;     // [R]
+  uint32_t* band;       // BAND: [R]
+  double rel_tol;       // BAND
 };
 
-// shared memory: RAW[2 buffers][2 sides][P][Tp] doubles
-template <int RPT>
+// shared memory: RAW[2 buffers][2 sides][P][Tp] elements of MT (cp.async target, read by the rows; fp32 means stay fp32 in
+// shared memory — half the bytes through the pipe that bounds this kernel — and are widened in registers).
+template <int RPT, typename MT, bool BAND>
 __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
   extern __shared__ __align__(16) double sm_d[];
+  const MT* const M2 = reinterpret_cast<const MT*>(A.M2);
   __shared__ int s_gs[8];
   __shared__ int s_extra;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
   const int T = A.T, Tp = A.Tp, P = A.P, nL = A.nL, nS = A.nS;
+  const double rt = A.rel_tol;
   if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
   if (tid == 0) {
     int extra = 0;
@@ -1270,14 +1433,14 @@ __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
   }
   int e_[RPT], r_[RPT], rid[RPT];
   double ob[RPT], th[RPT];
-  uint32_t cnt[RPT];
+  uint32_t cnt[RPT], bnd[RPT];
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     const int pos = rb + tid + q * nthr;
     rid[q] = (pos < re) ? A.srow[pos] : -1;
     e_[q] = r_[q] = 0;
     ob[q] = th[q] = 0.0;
-    cnt[q] = 0;
+    cnt[q] = bnd[q] = 0;
     if (rid[q] >= 0) {
       e_[q] = A.row_emit[rid[q]];
       r_[q] = A.row_recv[rid[q]];
@@ -1285,7 +1448,8 @@ __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
       th[q] = A.thr[rid[q]];
     }
   }
-  const int tile = P * Tp;  // doubles per (buffer, side)
+  const int tile = P * Tp;  // elements per (buffer, side)
+  MT* const rawbase = reinterpret_cast<MT*>(sm_d);
   const int n_tiles = (A.n_valid + P - 1) / P;
   __syncthreads();
   const int g_first[2] = {s_gs[0], s_gs[nL]};  // LIGAND_1 / RECEPTOR_1: always present
@@ -1295,12 +1459,12 @@ __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
   const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
   auto issue = [&](int t) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    double* dst0 = sm_d + (size_t)(t & 1) * 2 * tile;
+    MT* dst0 = rawbase + (size_t)(t & 1) * 2 * tile;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-      const double* src = A.M2 + (((size_t)ch * A.G + g_first[side]) * T) * 32 + lane0 + p_t;
-      double* dst = dst0 + side * tile + p_t * Tp;
-      for (int ct = ct0; ct < T; ct += ctstep) cp_async_8(dst + ct, src + (size_t)ct * 32);
+      const MT* src = M2 + (((size_t)ch * A.G + g_first[side]) * T) * 32 + lane0 + p_t;
+      MT* dst = dst0 + side * tile + p_t * Tp;
+      for (int ct = ct0; ct < T; ct += ctstep) cp_async_elem<MT>(dst + ct, src + (size_t)ct * 32);
     }
     cp_async_commit();
   };
@@ -1308,16 +1472,16 @@ __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
   for (int t = 0; t < n_tiles; ++t) {
     if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();  // tile t is in shared memory for every thread
-    double* raw = sm_d + (size_t)(t & 1) * 2 * tile;
+    MT* raw = rawbase + (size_t)(t & 1) * 2 * tile;
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    if (has_extra) {  // complexes: fold the extra subunits in
+    if (has_extra) {  // complexes: fold the extra subunits in (min of fp32 values is exact in fp32)
       for (int side = 0; side < 2; ++side) {
         const int s0 = side ? nL : 0, s1 = side ? nS : nL;
         for (int ct = ct0; ct < T; ct += ctstep) {
-          double m = raw[side * tile + p_t * Tp + ct];
+          MT m = raw[side * tile + p_t * Tp + ct];
           for (int s = s0 + 1; s < s1; ++s) {
             const int g = s_gs[s];
-            if (g >= 0) m = fmin(m, A.M2[(((size_t)ch * A.G + g) * T + ct) * 32 + lane0 + p_t]);
+            if (g >= 0) m = (MT)fmin((double)m, (double)M2[(((size_t)ch * A.G + g) * T + ct) * 32 + lane0 + p_t]);
           }
           raw[side * tile + p_t * Tp + ct] = m;
         }
@@ -1328,33 +1492,52 @@ __global__ void __launch_bounds__(256, 2) k_score_det(ScoreDetArgs A) {
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (rid[q] < 0) continue;
-      const double* pa = raw + e_[q];
-      const double* pbp = raw + tile + r_[q];
-      uint32_t c = 0;
+      const MT* pa = raw + e_[q];
+      const MT* pbp = raw + tile + r_[q];
+      uint32_t c = 0, bc = 0;
       if (A.score_type == 0) {
+        const double o2 = ob[q] * ob[q];
 #pragma unroll 4
-        for (int p = 0; p < pmax; ++p) c += (pa[p * Tp] * pbp[p * Tp] >= th[q]) ? 1u : 0u;
+        for (int p = 0; p < pmax; ++p) {
+          const double x = (double)pa[p * Tp] * (double)pbp[p * Tp];
+          c += (x >= th[q]) ? 1u : 0u;
+          if (BAND) bc += band_product(x, o2, rt) ? 1u : 0u;
+        }
       } else {
 #pragma unroll 4
-        for (int p = 0; p < pmax; ++p) c += ((pa[p * Tp] + pbp[p * Tp]) / 2 >= ob[q]) ? 1u : 0u;
+        for (int p = 0; p < pmax; ++p) {
+          const double sc = ((double)pa[p * Tp] + (double)pbp[p * Tp]) / 2;
+          c += (sc >= ob[q]) ? 1u : 0u;
+          if (BAND) bc += band_value(sc, ob[q], rt) ? 1u : 0u;
+        }
       }
       cnt[q] += c;
+      bnd[q] += bc;
     }
     __syncthreads();  // everyone is done with buffer t & 1 before it is overwritten
   }
 #pragma unroll
   for (int q = 0; q < RPT; ++q)
-    if (rid[q] >= 0) A.counts[rid[q]] += cnt[q];
+    if (rid[q] >= 0) {
+      A.counts[rid[q]] += cnt[q];
+      if (BAND) A.band[rid[q]] += bnd[q];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // K3, differential mode (production): same block / tile structure as k_score_det, for the 3 + nL + nR columns.
-//   * tiles are interleaved [side][replicate][cell type][pass*2 + cond]: a row reads its emitter's four ligand minima
-//     and its receiver's four receptor minima with two 16-byte loads each and no per-access index arithmetic;
+//   * fp64 tiles are four planes [pass][side][replicate][cell type][cond]: a row reads its emitter's ligand minima and its
+//     receiver's receptor minima of one pass with ONE 16-byte load each, and the rows of a warp (consecutive receivers)
+//     read consecutive 16-byte chunks: conflict-free. (With the four values of a cell type interleaved in 32 bytes, as in
+//     round 1, consecutive cell types were 32 bytes apart and every such load was a 2-way bank conflict: ncu counted
+//     17.4 G conflict wavefronts out of 35.0 G on config 5.) fp32 tiles keep [side][replicate][cell type][pass*2 + cond]:
+//     16 bytes per cell type, one load per side, widened to fp64 in registers;
 //   * FACT: the per-subunit columns |L_i / R_j cond2 - cond1| >= |observed| depend only on (LRI, emitter) resp.
 //     (LRI, receiver). When the observed subunit differences are bitwise equal across the rows that share that pair
 //     (always true for the reference's tables, checked on the host), they are counted once per (cell type, subunit) and
-//     added to the rows at the end instead of once per row;
+//     added to the rows at the end instead of once per row. The comparison happens in the fix-up pass, where the thread
+//     that owns (replicate, cell type) has the subunit's two pass-1 means in registers: the P lanes that share a cell type
+//     vote with one ballot and their first lane adds the count to a shared-memory counter that only it ever touches;
 //   * the DE column |sqrt(x2) - sqrt(x1)| >= |observed| is decided from rsqrt.approx when the approximation's error band
 //     cannot change the outcome (the band is 8x the documented 2^-20 relative error) and recomputed with the IEEE sqrt
 //     otherwise, so the decision is always the exact one.
@@ -1372,15 +1555,21 @@ __device__ __forceinline__ bool de_fast_range(double x) {
   return (hi - 0x05D00000u) < 0x74400000u || (hi | lo) == 0u;  // exponent field in [1023 - 930, 1023 + 930)
 }
 
-// exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0
-__device__ __forceinline__ bool de_exceeds(double x1, double x0, double aob) {
+// exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0. kslack = 2^-17 (8x the approximation's error), plus
+// 1.5 rel_tol with BAND, which widens the exactly-evaluated zone over the whole tolerance band: there bc also receives
+// the exact band_diff(sqrt(x1), sqrt(x0)) decision, and outside of it a comparison is provably not in the band.
+constexpr double kDeSlack = 7.62939453125e-06;  // 2^-17
+template <bool BAND>
+__device__ __forceinline__ bool de_exceeds(double x1, double x0, double aob, double kslack, double rt, uint32_t& bc) {
   // fmax keeps the approximation finite at x = 0 (0 * finite = 0 = sqrt(0)); inputs in (0, 1e-300) are out of the fast range
   const double s1 = x1 * rsqrt_approx(fmax(x1, 1e-300));
   const double s0 = x0 * rsqrt_approx(fmax(x0, 1e-300));
-  const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;  // 2^-17
+  const double d = fabs(s1 - s0), slack = (s1 + s0) * kslack;
   const bool yes = d - slack > aob, no = d + slack < aob;
   if (de_fast_range(x1) && de_fast_range(x0) && (yes || no)) return yes;
-  return fabs(sqrt(x1) - sqrt(x0)) >= aob;
+  const double e1 = sqrt(x1), e0 = sqrt(x0);
+  if (BAND) bc += band_diff(e1, e0, aob, rt) ? 1u : 0u;
+  return fabs(e1 - e0) >= aob;
 }
 
 // Self-test of de_exceeds against the plain IEEE expression on adversarial inputs (thresholds within a few ulps of the
@@ -1406,8 +1595,14 @@ __global__ void k_selftest_de(unsigned long long n, unsigned long long seed, uns
   else aob = exp2((w[2] * (1.0 / 4294967296.0) - 0.5) * span * 0.5);
   if (!(aob >= 0.0)) aob = 0.0;
   const bool want = truth >= aob;
-  const bool got = de_exceeds(x1, x0, aob);
+  uint32_t bc = 0, bc2 = 0;
+  const bool got = de_exceeds<false>(x1, x0, aob, kDeSlack, 0.0, bc);
   if (want != got) atomicAdd(&out[0], 1ull);
+  // BAND variant (rel_tol = 1e-5): same decision, and the band flag equals the exact band test
+  const double rt = 1e-5;
+  const bool got2 = de_exceeds<true>(x1, x0, aob, kDeSlack + 1.5 * rt, rt, bc2);
+  const bool want_band = band_diff(sqrt(x1), sqrt(x0), aob, rt);
+  if (want != got2 || (bc2 != 0) != want_band) atomicAdd(&out[0], 1ull);
   // was it decidable without the IEEE sqrt?
   const double s1 = (x1 == 0.0) ? 0.0 : x1 * rsqrt_approx(x1), s0 = (x0 == 0.0) ? 0.0 : x0 * rsqrt_approx(x0);
   const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;
@@ -1430,20 +1625,30 @@ struct ScoreDiffArgs {
   const double* obs;      // column-major [R][ncols], original row ids
   const double* thr;      // column-major [R][2]
   const double* obs_sub;  // FACT: [L][T][nS] common observed subunit differences (NaN = unused / absent)
-  const double* M1;
-  const double* M2;
+  const void* M1;         // element type MT
+  const void* M2;
   uint32_t* counts;
+  uint32_t* band;         // BAND
+  double rel_tol;         // BAND
 };
 
-template <int RPT, bool FACT>
+// shared memory: RAW[2 buffers] of MT, each fp64: [pass][side][P][Tp][cond], fp32: [side][P][Tp][pass*2 + cond]; then (doubles)
+// FACT: SO[T][nS] |observed subunit differences| + CNT[T][nS] (+ BND[T][nS]) uint32 counters; !FACT: DL[P][Tp][nL],
+// DR[P][Tp][nR] subunit differences (+ WL, WR: cond2 + cond1, the band's scale).
+template <int RPT, bool FACT, typename MT, bool BAND>
 __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
   extern __shared__ __align__(16) double sm_d[];
+  constexpr bool F32 = sizeof(MT) == 4;
+  const MT* const M1 = reinterpret_cast<const MT*>(A.M1);
+  const MT* const M2 = reinterpret_cast<const MT*>(A.M2);
   __shared__ int s_gs[8];
   __shared__ int s_extra;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
   const int T = A.T, Tp = A.Tp, P = A.P, K = A.K, nL = A.nL, nR = A.nR, nS = nL + nR;
   const int ncols = 3 + nS;
+  const double rt = A.rel_tol;
+  const double kslack = kDeSlack + (BAND ? 1.5 * rt : 0.0);
   if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
   if (tid == 0) {
     int extra = 0;
@@ -1454,7 +1659,7 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
   constexpr int NOB = FACT ? 3 : 11;
   int e_[RPT], r_[RPT], rid[RPT];
   double ob[RPT][NOB], th[RPT][2];
-  uint32_t cnt[RPT][NOB];
+  uint32_t cnt[RPT][NOB], bnd[RPT][BAND ? NOB : 1];
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     const int pos = rb + tid + q * nthr;
@@ -1462,6 +1667,8 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
     e_[q] = r_[q] = 0;
 #pragma unroll
     for (int c = 0; c < NOB; ++c) { ob[q][c] = 0.0; cnt[q][c] = 0; }
+#pragma unroll
+    for (int c = 0; c < (BAND ? NOB : 1); ++c) bnd[q][c] = 0;
     th[q][0] = th[q][1] = 0.0;
     if (rid[q] >= 0) {
       e_[q] = A.row_emit[rid[q]];
@@ -1473,20 +1680,30 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
       th[q][1] = A.thr[(size_t)A.R + rid[q]];
     }
   }
-  // FACT: (cell type, subunit) pairs owned by this thread for the whole launch: items tid and tid + nthr of T * nS
-  double so[2] = {0.0, 0.0};
-  uint32_t sc[2] = {0, 0};
+  const int plane = P * Tp * 2;                 // fp64: elements of one [pass][side] plane
+  const int sideStride = P * Tp * 4;            // fp32: elements per side
+  const int rawSize = 2 * sideStride;           // elements per RAW buffer (both layouts)
+  MT* const rawbase = reinterpret_cast<MT*>(sm_d);
+  // element (side, p, ct, k = pass * 2 + cond) of a RAW buffer
+  auto at = [&](int side, int p, int ct, int k) -> int {
+    return F32 ? side * sideStride + (p * Tp + ct) * 4 + k : ((k >> 1) * 2 + side) * plane + (p * Tp + ct) * 2 + (k & 1);
+  };
+  double* const tail = sm_d + (F32 ? rawSize : 2 * rawSize);  // after the two RAW buffers
+  // FACT tail: SO, CNT (BND); !FACT tail: DL, DR (WL, WR)
+  double* const SO = tail;
+  uint32_t* const CNT = reinterpret_cast<uint32_t*>(tail + T * nS);
+  uint32_t* const BND = CNT + T * nS;
+  double* const DL = tail;                      // [P][Tp][nL]
+  double* const DR = DL + P * Tp * nL;          // [P][Tp][nR]
+  double* const WL = DR + P * Tp * nR;
+  double* const WR = WL + P * Tp * nL;
   if (FACT) {
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const int item = tid + w * nthr;
-      so[w] = (item < T * nS) ? fabs(A.obs_sub[(size_t)l * T * nS + item]) : __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = tid; i < T * nS; i += nthr) {
+      SO[i] = fabs(A.obs_sub[(size_t)l * T * nS + i]);  // NaN (absent / unused): never exceeded, never in the band
+      CNT[i] = 0;
+      if (BAND) BND[i] = 0;
     }
   }
-  const int sideStride = P * Tp * 4;            // doubles per side inside one RAW buffer
-  const int rawSize = 2 * sideStride;           // doubles per RAW buffer
-  double* const DL = sm_d + 2 * rawSize;        // [P][Tp][nL]
-  double* const DR = DL + P * Tp * nL;          // [P][Tp][nR]
   const int n_tiles = (A.n_valid + P - 1) / P;
   __syncthreads();
   const int g_first[2] = {s_gs[0], s_gs[nL]};
@@ -1494,137 +1711,185 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
   // thread -> (replicate p, cell type ct0 + k * ctstep) without integer divisions (P is a power of two)
   const int lgP = 31 - __clz(P);
   const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
+  const int n_ct_iter = (T + ctstep - 1) / ctstep;   // uniform trip count: the fix-up pass votes with full-warp ballots
+  const uint32_t gmask = ((P >= 32) ? 0xffffffffu : ((1u << P) - 1u)) << (lane & ~(P - 1) & 31);
+  const bool gleader = (lane & (P - 1) & 31) == 0;
   auto issue = [&](int t) {
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    double* dst0 = sm_d + (size_t)(t & 1) * rawSize;
+    MT* dst0 = rawbase + (size_t)(t & 1) * rawSize;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const double* src = ((k >> 1) ? A.M2 : A.M1) + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T) * 32 + lane0 + p_t;
-        double* dst = dst0 + side * sideStride + p_t * Tp * 4 + k;
-        for (int ct = ct0; ct < T; ct += ctstep) cp_async_8(dst + ct * 4, src + (size_t)ct * 32);
+        const MT* src = ((k >> 1) ? M2 : M1) + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T) * 32 + lane0 + p_t;
+        MT* dst = dst0 + at(side, p_t, 0, k);
+        const int cstep = F32 ? 4 : 2;
+        for (int ct = ct0; ct < T; ct += ctstep) cp_async_elem<MT>(dst + ct * cstep, src + (size_t)ct * 32);
       }
     }
     cp_async_commit();
   };
-  // FACT: decomposition of this thread's (cell type, subunit) items, once
-  const double* fact_ptr[2] = {nullptr, nullptr};
-  int fact_stride[2] = {0, 0};
-  if (FACT) {
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const int item = tid + w * nthr;
-      if (item < T * nS) {
-        const int ct = item / nS, sx = item % nS;
-        const int nSide = (sx < nL) ? nL : nR;
-        fact_ptr[w] = ((sx < nL) ? DL : DR) + ct * nSide + ((sx < nL) ? sx : sx - nL);
-        fact_stride[w] = Tp * nSide;
-      }
-    }
-  }
   if (n_tiles > 0) issue(0);
   for (int t = 0; t < n_tiles; ++t) {
     if (t + 1 < n_tiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    double* raw = sm_d + (size_t)(t & 1) * rawSize;
+    MT* raw = rawbase + (size_t)(t & 1) * rawSize;
     const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
-    // ---------------- fix-up: first-subunit differences, extra subunits of complexes folded in ----------------
-    for (int side = 0; side < 2; ++side) {
-     for (int ct = ct0; ct < T; ct += ctstep) {
-      const int p = p_t;
-      const int s0 = side ? nL : 0, nSide = side ? nR : nL;
-      double* b4 = raw + side * sideStride + (p * Tp + ct) * 4;  // {pass1 c1, pass1 c2, pass2 c1, pass2 c2}
-      double* dd = (side ? DR : DL) + (p * Tp + ct) * nSide;
-      double m10 = b4[0], m11 = b4[1], m20 = b4[2], m21 = b4[3];
-      dd[0] = m11 - m10;  // cond2 - cond1 (reference R/utils_cci.R:212-239)
-      for (int k = 1; k < nSide; ++k) {
-        const int g = s_gs[s0 + k];
-        double d = 0.0;
-        if (g >= 0) {
-          const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
-          const double a10 = A.M1[i0], a11 = A.M1[i1], a20 = A.M2[i0], a21 = A.M2[i1];
-          d = a11 - a10;
-          m10 = fmin(m10, a10); m11 = fmin(m11, a11); m20 = fmin(m20, a20); m21 = fmin(m21, a21);
-        }
-        dd[k] = d;
-      }
-      if (has_extra) { b4[0] = m10; b4[1] = m11; b4[2] = m20; b4[3] = m21; }
-     }
-    }
-    __syncthreads();
     const int pmax = min(P, A.n_valid - pb);
-    // ---------------- subunit columns, once per (cell type, subunit) ----------------
-    if (FACT) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (fact_ptr[w]) {
-          const double* pd = fact_ptr[w];
-          const int stride = fact_stride[w];
-          uint32_t c = 0;
-          for (int p = 0; p < pmax; ++p) c += (fabs(pd[p * stride]) >= so[w]) ? 1u : 0u;
-          sc[w] += c;
+    const bool pvalid = p_t < pmax;
+    // -------- fix-up: subunit differences (counted here when FACT), extra subunits of complexes folded in --------
+    if (FACT || has_extra) {
+      for (int side = 0; side < 2; ++side) {
+        const int s0 = side ? nL : 0, nSide = side ? nR : nL;
+        for (int it = 0; it < n_ct_iter; ++it) {
+          const int ct_raw = ct0 + it * ctstep;
+          const bool ok = ct_raw < T;
+          const int ct = ok ? ct_raw : 0;
+          const int p = p_t;
+          MT m10 = raw[at(side, p, ct, 0)], m11 = raw[at(side, p, ct, 1)], m20 = raw[at(side, p, ct, 2)], m21 = raw[at(side, p, ct, 3)];
+          if (FACT) {
+            const double d10 = (double)m10, d11 = (double)m11;
+            const double so = SO[ct * nS + s0];
+            const uint32_t v = __ballot_sync(0xffffffffu, ok && pvalid && fabs(d11 - d10) >= so);  // cond2 - cond1 (R/utils_cci.R:212-239)
+            uint32_t vb = 0;
+            if (BAND) vb = __ballot_sync(0xffffffffu, ok && pvalid && band_diff(d11, d10, so, rt));
+            if (gleader && ok) {
+              CNT[ct * nS + s0] += __popc(v & gmask);
+              if (BAND) BND[ct * nS + s0] += __popc(vb & gmask);
+            }
+          }
+          for (int k = 1; k < nSide; ++k) {
+            const int g = s_gs[s0 + k];  // block-uniform
+            if (g >= 0) {
+              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
+              const MT a10 = M1[i0], a11 = M1[i1], a20 = M2[i0], a21 = M2[i1];
+              m10 = a10 < m10 ? a10 : m10; m11 = a11 < m11 ? a11 : m11;   // means are never NaN: plain minimum
+              m20 = a20 < m20 ? a20 : m20; m21 = a21 < m21 ? a21 : m21;
+              if (FACT) {
+                const double d10 = (double)a10, d11 = (double)a11;
+                const double so = SO[ct * nS + s0 + k];
+                const uint32_t v = __ballot_sync(0xffffffffu, ok && pvalid && fabs(d11 - d10) >= so);
+                uint32_t vb = 0;
+                if (BAND) vb = __ballot_sync(0xffffffffu, ok && pvalid && band_diff(d11, d10, so, rt));
+                if (gleader && ok) {
+                  CNT[ct * nS + s0 + k] += __popc(v & gmask);
+                  if (BAND) BND[ct * nS + s0 + k] += __popc(vb & gmask);
+                }
+              }
+            }
+          }
+          if (ok && has_extra) {
+            raw[at(side, p, ct, 0)] = m10; raw[at(side, p, ct, 1)] = m11; raw[at(side, p, ct, 2)] = m20; raw[at(side, p, ct, 3)] = m21;
+          }
         }
       }
     }
-    // ---------------- stage B: rows ----------------
+    if (!FACT) {  // subunit differences per (replicate, cell type) for the per-row comparison (tables not built the reference's way)
+      for (int side = 0; side < 2; ++side) {
+        const int s0 = side ? nL : 0, nSide = side ? nR : nL;
+        for (int ct = ct0; ct < T; ct += ctstep) {
+          const int p = p_t;
+          double* dd = (side ? DR : DL) + (p * Tp + ct) * nSide;
+          double* ww = (side ? WR : WL) + (p * Tp + ct) * nSide;
+          for (int k = 0; k < nSide; ++k) {
+            const int g = s_gs[s0 + k];
+            double d = 0.0, w = 0.0;
+            if (g >= 0) {
+              const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
+              const double a10 = (double)M1[i0], a11 = (double)M1[i1];
+              d = a11 - a10;
+              w = a11 + a10;
+            }
+            dd[k] = d;
+            if (BAND) ww[k] = w;
+          }
+        }
+      }
+    }
+    if (has_extra || !FACT) __syncthreads();  // tile / D-tile writes of the fix-up are visible to the rows
+    // ---------------- rows ----------------
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (rid[q] < 0) continue;
-      const double2* pa = reinterpret_cast<const double2*>(raw + e_[q] * 4);
-      const double2* pbp = reinterpret_cast<const double2*>(raw + sideStride + r_[q] * 4);
       const double aob0 = fabs(ob[q][0]);
-      const int st2 = Tp * 2;  // double2 per replicate
-      uint32_t c0 = 0, c1 = 0, c2 = 0;
+      const double o2a = ob[q][1] * ob[q][1], o2b = ob[q][2] * ob[q][2];
+      uint32_t c0 = 0, c1 = 0, c2 = 0, b0 = 0, b1 = 0, b2 = 0;
 #pragma unroll 2
       for (int p = 0; p < pmax; ++p) {
-        const double2 a1 = pa[p * st2], a2 = pa[p * st2 + 1];
-        const double2 b1 = pbp[p * st2], b2 = pbp[p * st2 + 1];
-        if (A.score_type == 0) {
-          c0 += de_exceeds(a1.y * b1.y, a1.x * b1.x, aob0) ? 1u : 0u;
-          c1 += (a2.x * b2.x >= th[q][0]) ? 1u : 0u;
-          c2 += (a2.y * b2.y >= th[q][1]) ? 1u : 0u;
+        double2 a1, a2, b1v, b2v;   // emitter / receiver minima: pass 1 (c1, c2), pass 2 (c1, c2)
+        if (F32) {
+          const float4 fa = reinterpret_cast<const float4*>(raw)[p * Tp + e_[q]];
+          const float4 fb = reinterpret_cast<const float4*>(raw + sideStride)[p * Tp + r_[q]];
+          a1 = make_double2((double)fa.x, (double)fa.y); a2 = make_double2((double)fa.z, (double)fa.w);
+          b1v = make_double2((double)fb.x, (double)fb.y); b2v = make_double2((double)fb.z, (double)fb.w);
         } else {
-          const double de = (a1.y + b1.y) / 2 - (a1.x + b1.x) / 2;
+          const double2* pl = reinterpret_cast<const double2*>(raw);
+          const int pl2 = plane / 2;  // double2 per plane
+          a1 = pl[0 * pl2 + p * Tp + e_[q]];
+          b1v = pl[1 * pl2 + p * Tp + r_[q]];
+          a2 = pl[2 * pl2 + p * Tp + e_[q]];
+          b2v = pl[3 * pl2 + p * Tp + r_[q]];
+        }
+        if (A.score_type == 0) {
+          c0 += de_exceeds<BAND>(a1.y * b1v.y, a1.x * b1v.x, aob0, kslack, rt, b0) ? 1u : 0u;
+          const double xa = a2.x * b2v.x, xb = a2.y * b2v.y;
+          c1 += (xa >= th[q][0]) ? 1u : 0u;
+          c2 += (xb >= th[q][1]) ? 1u : 0u;
+          if (BAND) {
+            b1 += band_product(xa, o2a, rt) ? 1u : 0u;
+            b2 += band_product(xb, o2b, rt) ? 1u : 0u;
+          }
+        } else {
+          const double sc1 = (a1.y + b1v.y) / 2, sc0 = (a1.x + b1v.x) / 2;
+          const double de = sc1 - sc0;
+          const double sa = (a2.x + b2v.x) / 2, sb = (a2.y + b2v.y) / 2;
           c0 += (fabs(de) >= aob0) ? 1u : 0u;
-          c1 += ((a2.x + b2.x) / 2 >= ob[q][1]) ? 1u : 0u;
-          c2 += ((a2.y + b2.y) / 2 >= ob[q][2]) ? 1u : 0u;
+          c1 += (sa >= ob[q][1]) ? 1u : 0u;
+          c2 += (sb >= ob[q][2]) ? 1u : 0u;
+          if (BAND) {
+            b0 += band_diff(sc1, sc0, aob0, rt) ? 1u : 0u;
+            b1 += band_value(sa, ob[q][1], rt) ? 1u : 0u;
+            b2 += band_value(sb, ob[q][2], rt) ? 1u : 0u;
+          }
         }
         if (!FACT) {
           const double* dl = DL + (p * Tp + e_[q]) * nL;
           const double* dr = DR + (p * Tp + r_[q]) * nR;
+          const double* wl = WL + (p * Tp + e_[q]) * nL;
+          const double* wr = WR + (p * Tp + r_[q]) * nR;
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
             if (s < nS) {
               const double d = (s < nL) ? dl[s] : dr[s - nL];
-              cnt[q][FACT ? 0 : 3 + s] += (fabs(d) >= fabs(ob[q][FACT ? 0 : 3 + s])) ? 1u : 0u;
+              const double ao = fabs(ob[q][FACT ? 0 : 3 + s]);
+              cnt[q][FACT ? 0 : 3 + s] += (fabs(d) >= ao) ? 1u : 0u;
+              if (BAND) {
+                const double w = (s < nL) ? wl[s] : wr[s - nL];
+                bnd[q][(FACT || !BAND) ? 0 : 3 + s] += (fabs(fabs(d) - ao) <= rt * w) ? 1u : 0u;
+              }
             }
           }
         }
       }
       cnt[q][0] += c0; cnt[q][1] += c1; cnt[q][2] += c2;
+      if (BAND) { bnd[q][0] += b0; bnd[q][BAND ? 1 : 0] += b1; bnd[q][BAND ? 2 : 0] += b2; }
     }
     __syncthreads();  // everyone is done with RAW buffer t & 1 and the D tiles before they are overwritten
-  }
-  uint32_t* s_sub = reinterpret_cast<uint32_t*>(sm_d);  // [T][nS], reuses the tile memory
-  if (FACT) {
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const int item = tid + w * nthr;
-      if (item < T * nS) s_sub[item] = sc[w];
-    }
-    __syncthreads();
   }
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     if (rid[q] < 0) continue;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
+    for (int c = 0; c < 3; ++c) {
+      A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
+      if (BAND) A.band[(size_t)c * A.R + rid[q]] += bnd[q][BAND ? c : 0];
+    }
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
       if (s < nS) {
-        const uint32_t add = FACT ? s_sub[((s < nL) ? e_[q] : r_[q]) * nS + s] : cnt[q][FACT ? 0 : 3 + s];
-        A.counts[(size_t)(3 + s) * A.R + rid[q]] += add;
+        const int fi = ((s < nL) ? e_[q] : r_[q]) * nS + s;
+        A.counts[(size_t)(3 + s) * A.R + rid[q]] += FACT ? CNT[fi] : cnt[q][FACT ? 0 : 3 + s];
+        if (BAND) A.band[(size_t)(3 + s) * A.R + rid[q]] += FACT ? BND[fi] : bnd[q][(FACT || !BAND) ? 0 : 3 + s];
       }
     }
   }
@@ -1736,6 +2001,12 @@ __global__ void k_observed_rows(ObservedArgs A) {
 __global__ void k_widen_counts(size_t n, const uint32_t* __restrict__ in, long long* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (long long)in[i];
+}
+
+// multi-GPU merge without NCCL: acc += add (a peer's counters copied over NVLink)
+__global__ void k_add_counts(size_t n, const uint32_t* __restrict__ add, uint32_t* __restrict__ acc) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += add[i];
 }
 
 }  // namespace scdc

@@ -87,14 +87,15 @@ class PermutationProblem:
 
 
 def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-             n_cells, keep, device_base=0, stream=None, interrupt=None):
+             n_cells, keep, device_base=0, stream=None, interrupt=None, precision="fp64", rel_tol=0.0):
     o = Options()
     o.iterations = int(iterations)
     o.seed = int(seed) & (2**64 - 1)
     o.perm_offset = int(perm_offset)
     o.score_type = SCORE_TYPES[score_type] if isinstance(score_type, str) else int(score_type)
     o.n_gpus = int(n_gpus)
-    o.precision = 0
+    o.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    o.rel_tol = float(rel_tol)
     o.batch_size = int(batch_size)
     for name, lab in (("perm_cond", perm_cond), ("perm_ct", perm_ct)):
         if lab is not None:
@@ -113,10 +114,15 @@ def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm
     return o
 
 
-def _finish(problem, counts_f, dist, stats):
+def _finish(problem, counts_f, dist, stats, band_f=None):
+    na = counts_f == np.uint64(_lib.SCDC_COUNT_NA)
     counts = counts_f.astype(np.float64)
-    counts[counts_f == np.uint64(_lib.SCDC_COUNT_NA)] = np.nan
-    return {"counts": counts, "counts_raw": counts_f, "distributions": dist, "stats": stats.as_dict()}
+    counts[na] = np.nan
+    band = None
+    if band_f is not None:
+        band = band_f.astype(np.float64)
+        band[na] = np.nan
+    return {"counts": counts, "counts_raw": counts_f, "band_counts": band, "distributions": dist, "stats": stats.as_dict()}
 
 
 def device_count() -> int:
@@ -133,24 +139,59 @@ def version() -> str:
 
 
 def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="geometric_mean", n_gpus=1, perm_offset=0,
-                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0, interrupt=None):
+                batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0, interrupt=None,
+                precision="fp64", rel_tol=0.0):
     """One-shot `scdc_perm_counts` with HOST buffers (what the `.Call` wrapper does). Returns dict(counts [R_sub, ncols]
-    float64 with NaN = NA, distributions or None, stats)."""
+    float64 with NaN = NA, band_counts (precision="fp32_fast": comparisons inside the tolerance band) or None,
+    distributions or None, stats)."""
     lib = _lib.load()
     keep = []
     p = problem.c_struct()
     o = _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm_cond, perm_ct, return_distributions,
-                 problem.n_cells, keep, device_base=device_base, interrupt=interrupt)
+                 problem.n_cells, keep, device_base=device_base, interrupt=interrupt, precision=precision, rel_tol=rel_tol)
     counts = np.zeros((problem.n_rows, problem.ncols), dtype=np.uint64, order="F")
     res = Result()
     res.counts = _ptr(counts)
+    band = None
+    if o.precision != 0:
+        band = np.zeros((problem.n_rows, problem.ncols), dtype=np.uint64, order="F")
+        res.band_counts = _ptr(band)
     dist = None
     if return_distributions:
         ncd = 3 if problem.n_conditions == 2 else 1
         dist = np.zeros((int(iterations), ncd, problem.n_rows), dtype=np.float64)
         res.distributions = _ptr(dist)
     check(lib.scdc_perm_counts(C.byref(p), C.byref(o), C.byref(res)))
-    return _finish(problem, counts, dist, res.stats)
+    return _finish(problem, counts, dist, res.stats, band)
+
+
+def cci_template(n_celltypes, n_conditions, lri_order, ct_code, cond_code=None):
+    """`scdc_cci_template` (create_cci_template + add_cell_number, R/utils_cci.R:1-169, integer-coded): returns
+    (emitter, receiver, lri_idx) int32 [T*T*L] and (ncells_emitter, ncells_receiver) int32 [C, T*T*L]."""
+    lib = _lib.load()
+    order = _arr(lri_order, np.int32)
+    T, Cn, L = int(n_celltypes), int(n_conditions), len(order)
+    n = T * T * L
+    em, rc, li = (np.empty(n, dtype=np.int32) for _ in range(3))
+    ne, nr = np.empty((Cn, n), dtype=np.int32), np.empty((Cn, n), dtype=np.int32)
+    ct, cd = _arr(ct_code, np.int32), _arr(cond_code, np.int32)
+    check(lib.scdc_cci_template(T, Cn, L, _ptr(order), len(ct), _ptr(ct), _ptr(cd), _ptr(em), _ptr(rc), _ptr(li), _ptr(ne), _ptr(nr)))
+    return em, rc, li, ne, nr
+
+
+def merge_pvalues(n_full, tested_rows, counts_raw, iterations, sub_gene=None, lri_idx=None, max_nL=1, max_nR=1):
+    """`scdc_merge_pvalues` (R/utils_permutation.R:215-259 + 427-469): counts_raw uint64 [R_sub, ncols] (SCDC_COUNT_NA = NA) ->
+    p-values float64 [n_full, ncols] with 1 outside the tested rows and NaN for absent subunits."""
+    lib = _lib.load()
+    counts = np.asfortranarray(counts_raw, dtype=np.uint64)
+    n_tested, ncols = counts.shape
+    rows = _arr(tested_rows, np.int64)
+    out = np.empty((int(n_full), ncols), dtype=np.float64, order="F")
+    sg = None if sub_gene is None else _arr(sub_gene, np.int32)
+    li = None if lri_idx is None else _arr(lri_idx, np.int32)
+    check(lib.scdc_merge_pvalues(int(n_full), n_tested, _ptr(rows), ncols, _ptr(counts), int(iterations),
+                                 0 if sg is None else sg.shape[0], int(max_nL), int(max_nR), _ptr(sg), _ptr(li), _ptr(out)))
+    return out
 
 
 class Engine:
@@ -182,16 +223,21 @@ class Engine:
 
     def run(self, iterations, seed=42, score_type="geometric_mean", perm_offset=0, batch_size=0, perm_cond=None,
             perm_ct=None, return_distributions=False, counts_device_ptr=None, want_host_counts=True, stream=None,
-            interrupt=None):
+            interrupt=None, precision="fp64", rel_tol=0.0, band_device_ptr=None):
         keep = []
         pr = self.problem
         o = _options(iterations, seed, score_type, perm_offset, 1, batch_size, perm_cond, perm_ct, return_distributions,
-                     pr.n_cells, keep, stream=stream, interrupt=interrupt)
+                     pr.n_cells, keep, stream=stream, interrupt=interrupt, precision=precision, rel_tol=rel_tol)
         res = Result()
-        counts = None
+        counts = band = None
         if want_host_counts:
             counts = np.zeros((pr.n_rows, pr.ncols), dtype=np.uint64, order="F")
             res.counts = _ptr(counts)
+            if o.precision != 0:
+                band = np.zeros((pr.n_rows, pr.ncols), dtype=np.uint64, order="F")
+                res.band_counts = _ptr(band)
+        if band_device_ptr is not None:
+            res.band_device = C.c_void_p(int(band_device_ptr))
         if counts_device_ptr is not None:
             res.counts_device = C.c_void_p(int(counts_device_ptr))
         dist = None
@@ -202,7 +248,7 @@ class Engine:
         check(self._lib.scdc_run(self._h, C.byref(o), C.byref(res)))
         if counts is None:
             return {"counts": None, "distributions": dist, "stats": res.stats.as_dict()}
-        return _finish(pr, counts, dist, res.stats)
+        return _finish(pr, counts, dist, res.stats, band)
 
     def group_means(self, detection_rate=False):
         """aggregate_cells on the original labels (R/utils_cci.R:441-462): [K, G] means (and detection rates)."""

@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import cci as _cci
-from .engine import PermutationProblem, perm_counts
+from .engine import PermutationProblem, merge_pvalues, perm_counts
 
 INTERNAL_ITER = 1000   # R/utils_permutation.R:10
 
@@ -130,17 +130,19 @@ def run_stat_analysis(analysis_inputs, cci_dt_simple, iterations, return_distrib
     else:
         res = engine.run(n_run, seed=seed, score_type=score_type, batch_size=batch_size, perm_cond=perm_cond,
                          perm_ct=perm_ct, return_distributions=return_distributions)
-    pvals = res["counts"] / iterations                  # :215-259 (NaN where the subunit is NA, :442-469)
+    # p = counts / iterations (:215-259) and the merge-back (:427-469: 1 outside the tested rows, NA for absent subunits),
+    # integer-coded in the shim (`scdc_merge_pvalues`, SURVEY.md "next" item f3)
     out = dict(cci_dt_simple)
     n_full = len(mask)
+    raw = res.get("counts_raw")
+    if raw is None:     # counts given as floats with NaN = NA (test doubles of the device call)
+        c = np.asarray(res["counts"], dtype=np.float64)
+        raw = np.where(np.isnan(c), np.float64(0), c).astype(np.uint64)
+        raw[np.isnan(c)] = np.uint64(2**64 - 1)
+    pv = merge_pvalues(n_full, np.flatnonzero(mask), raw, iterations, sub_gene=_cci.encode_inputs(ai)["sub_gene"],
+                       lri_idx=np.asarray(cci_dt_simple["LRI_IDX"]), max_nL=ai["max_nL"], max_nR=ai["max_nR"])
     for k, name in enumerate(pvalue_column_names(ai)):
-        col = np.ones(n_full)                           # rows outside the tested subset get 1 (:434-441)
-        col[mask] = pvals[:, k]
-        if name[0] in "LR" and name[1].isdigit():       # subunit p-values are NA where the subunit is NA (:442-469)
-            s = (int(name[1]) - 1) if name[0] == "L" else ai["max_nL"] + int(name[1]) - 1
-            enc_na = _cci.encode_inputs(ai)["sub_gene"][np.asarray(cci_dt_simple["LRI_IDX"]), s] < 0
-            col[enc_na] = np.nan
-        out[name] = col
+        out[name] = np.ascontiguousarray(pv[:, k])
     distributions = {}
     if return_distributions:                            # :304-426: rows x (iterations + 1), last column = observed
         d = res["distributions"]                        # [iterations, ncols_d, R_sub]

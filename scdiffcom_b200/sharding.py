@@ -25,9 +25,10 @@ def merge_counts(counts, group=None):
 
 
 def run_sharded(engine, iterations, counts_dev, *, seed=42, score_type="geometric_mean", batch_size=0, stream=None,
-                group=None):
+                group=None, precision="fp64", rel_tol=0.0, band_dev=None):
     """Run this rank's shard of `iterations` replicates on `engine` (its GPU), leave the merged int64 counters in the
-    torch CUDA tensor `counts_dev` on every rank. Returns the engine stats of the local shard."""
+    torch CUDA tensor `counts_dev` on every rank (and the band counters of precision="fp32_fast" in `band_dev`, if given).
+    Returns the engine stats of the local shard."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -35,8 +36,14 @@ def run_sharded(engine, iterations, counts_dev, *, seed=42, score_type="geometri
     stats = None
     if n > 0:
         stats = engine.run(n, seed=seed, score_type=score_type, perm_offset=begin, batch_size=batch_size,
-                           counts_device_ptr=counts_dev.data_ptr(), want_host_counts=False, stream=stream)["stats"]
+                           counts_device_ptr=counts_dev.data_ptr(), want_host_counts=False, stream=stream,
+                           precision=precision, rel_tol=rel_tol,
+                           band_device_ptr=None if band_dev is None else band_dev.data_ptr())["stats"]
     else:
         counts_dev.zero_()
+        if band_dev is not None:
+            band_dev.zero_()
     merge_counts(counts_dev, group)
+    if band_dev is not None:
+        merge_counts(band_dev, group)
     return stats

@@ -11,9 +11,13 @@
 # src/scdc_rcall.c and is kept next to it.
 
 scdc_counts_b200 <- function(analysis_inputs, sub_cci_template_iter, observed, iterations, score_type,
-                             return_distributions, seed = 42L, n_gpus = 0L) {
+                             return_distributions, seed = 42L, n_gpus = 0L, precision = "fp64", rel_tol = 0) {
   data_tr <- analysis_inputs$data_tr                       # cells x genes dgCMatrix, already gene-subset (:79-84)
   cell_types <- analysis_inputs$cell_types
+  n_groups <- length(cell_types) * (if (analysis_inputs$condition$is_cond) 2L else 1L)
+  if (n_groups > 254L) {                                   # 8-bit group codes on the device (include/scdc.h)
+    stop("scDiffCom B200 backend: more than 254 (cell type x condition) groups; use the R backend")
+  }
   ct <- match(analysis_inputs$metadata$cell_type, cell_types) - 1L
   cond <- NULL
   if (analysis_inputs$condition$is_cond) {
@@ -21,20 +25,30 @@ scdc_counts_b200 <- function(analysis_inputs, sub_cci_template_iter, observed, i
   }
   LR_COLNAMES <- c(paste0("LIGAND_", 1:analysis_inputs$max_nL), paste0("RECEPTOR_", 1:analysis_inputs$max_nR))
   LRI <- analysis_inputs$LRI
-  sub_gene <- t(sapply(LR_COLNAMES, function(col) {
-    g <- match(LRI[[col]], colnames(data_tr)) - 1L
-    g[is.na(g)] <- -1L
-    g
-  }))                                                      # (max_nL + max_nR) x n_LRI, 0-based, NA -> -1
+  n_lri <- nrow(LRI)
+  sub_gene <- matrix(                                      # (max_nL + max_nR) x n_LRI, 0-based, NA -> -1
+    unlist(lapply(LR_COLNAMES, function(col) {             # (explicit shape: sapply() + t() collapses when n_LRI == 1)
+      g <- match(LRI[[col]], colnames(data_tr)) - 1L
+      g[is.na(g)] <- -1L
+      as.integer(g)
+    })),
+    nrow = length(LR_COLNAMES), ncol = n_lri, byrow = TRUE
+  )
   storage.mode(sub_gene) <- "integer"
-  rows <- cbind(
-    match(sub_cci_template_iter$LRI, LRI$LRI) - 1L,
-    match(sub_cci_template_iter$EMITTER_CELLTYPE, cell_types) - 1L,
-    match(sub_cci_template_iter$RECEIVER_CELLTYPE, cell_types) - 1L
+  rows <- matrix(
+    c(match(sub_cci_template_iter$LRI, LRI$LRI) - 1L,
+      match(sub_cci_template_iter$EMITTER_CELLTYPE, cell_types) - 1L,
+      match(sub_cci_template_iter$RECEIVER_CELLTYPE, cell_types) - 1L),
+    ncol = 3
   )
   storage.mode(rows) <- "integer"
+  observed <- as.matrix(observed)
+  storage.mode(observed) <- "double"
+  stopifnot(is.numeric(iterations), length(iterations) == 1L, !is.na(iterations), iterations >= 1,
+            is.numeric(seed), length(seed) == 1L, !is.na(seed), seed >= 0)
   opts <- list(
-    iterations = iterations, seed = seed, n_gpus = n_gpus,
+    iterations = as.numeric(iterations), seed = as.numeric(seed), n_gpus = as.integer(n_gpus),
+    precision = if (identical(precision, "fp32_fast")) 1L else 0L, rel_tol = as.numeric(rel_tol),
     score_type = if (score_type == "geometric_mean") 0L else 1L,
     n_celltypes = length(cell_types), max_nL = analysis_inputs$max_nL, max_nR = analysis_inputs$max_nR,
     return_distributions = as.integer(return_distributions),
@@ -42,7 +56,8 @@ scdc_counts_b200 <- function(analysis_inputs, sub_cci_template_iter, observed, i
   )
   .Call(
     "C_scdc_perm_counts",
-    data_tr@p, data_tr@i, data_tr@x, data_tr@Dim, ct, cond, sub_gene, rows, observed, opts,
+    as.integer(data_tr@p), as.integer(data_tr@i), as.numeric(data_tr@x), as.integer(data_tr@Dim),
+    as.integer(ct), if (is.null(cond)) NULL else as.integer(cond), sub_gene, rows, observed, opts,
     PACKAGE = "scDiffCom"
   )
 }
@@ -61,5 +76,11 @@ scdc_counts_b200 <- function(analysis_inputs, sub_cci_template_iter, observed, i
 #     array_counts <- scdc_counts_b200(analysis_inputs, sub_cci_template_iter, observed, n_run, score_type, FALSE,
 #                                      seed = <seed of run_interaction_analysis>)
 #     n_broad_iter <- 1          # array_counts is already summed over batches: lines 215-259 then divide by `iterations`
-#     if (analysis_inputs$condition$is_cond) dim(array_counts) <- c(nrow(array_counts), ncol(array_counts), 1)
+#     if (analysis_inputs$condition$is_cond) {
+#       array_counts <- array(as.vector(array_counts), dim = c(nrow(array_counts), ncol(array_counts), 1))
+#     } else {
+#       array_counts <- as.vector(array_counts)   # plain vector (no dim, no "stats" attribute): `P_VALUE := pvals` at :215-221
+#     }
 #   } else { <original sapply(...) loop> }
+# getOption("scDiffCom.b200.precision", "fp64") / getOption("scDiffCom.b200.rel_tol", 0) select SCDC_FP32_FAST the same
+# out-of-band way; the band counters come back as attr(array_counts, "band_counts") (read it before as.vector()).

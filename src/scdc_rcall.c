@@ -30,6 +30,13 @@ static double opt_num(SEXP opts, const char* name, double dflt) {
   return Rf_isNull(v) ? dflt : Rf_asReal(v);
 }
 
+/* a finite number in [lo, hi], else an R error naming the option (NA, NaN, negative seeds ... never reach a C cast) */
+static double opt_checked(SEXP opts, const char* name, double dflt, double lo, double hi) {
+  const double v = opt_num(opts, name, dflt);
+  if (ISNAN(v) || v < lo || v > hi) Rf_error("C_scdc_perm_counts: option '%s' must be a number in [%g, %g]", name, lo, hi);
+  return v;
+}
+
 /*
  * .Call("C_scdc_perm_counts", p, i, x, dim, ct, cond, sub_gene, rows, observed, opts)
  *   p, i, x   data_tr@p, data_tr@i, data_tr@x of the cells x genes dgCMatrix (after R/utils_permutation.R:79-84)
@@ -40,9 +47,11 @@ static double opt_num(SEXP opts, const char* name, double dflt) {
  *   rows      integer matrix R_sub x 3: LRI index (0-based column of sub_gene), emitter code, receiver code
  *   observed  double matrix R_sub x ncols in the column order of R/utils_permutation.R:580-598 (NA allowed)
  *   opts      list(iterations, seed, score_type = 0L|1L, n_gpus, n_celltypes, max_nL, max_nR, return_distributions,
+ *                  precision = 0L (fp64-exact) | 1L (fp32-fast), rel_tol,
  *                  perm_cond = raw matrix N x iterations | NULL, perm_ct = raw matrix N x iterations | NULL)
  * Returns a double matrix R_sub x ncols of exceedance counts (NA_real_ where the subunit is NA), with attributes
- * "stats" (named numeric) and, when requested, "distributions" (double array R_sub x ncols_d x iterations).
+ * "stats" (named numeric), "band_counts" (fp32-fast: double matrix R_sub x ncols, comparisons inside the tolerance band)
+ * and, when requested, "distributions" (double array R_sub x ncols_d x iterations).
  */
 /* scdc_options.interrupt: R_CheckUserInterrupt() longjmps when the user pressed Ctrl-C / Esc, which must not unwind through
  * the engine's C++ frames; under R_ToplevelExec the jump is caught and reported as FALSE instead. The engine then stops
@@ -59,10 +68,18 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   memset(&opt, 0, sizeof opt);
   memset(&res, 0, sizeof res);
   if (TYPEOF(p) != INTSXP || TYPEOF(i) != INTSXP || TYPEOF(x) != REALSXP || TYPEOF(ct) != INTSXP ||
-      TYPEOF(sub_gene) != INTSXP || TYPEOF(rows) != INTSXP || TYPEOF(observed) != REALSXP)
+      TYPEOF(sub_gene) != INTSXP || TYPEOF(rows) != INTSXP || TYPEOF(observed) != REALSXP || TYPEOF(dim) != INTSXP ||
+      (!Rf_isNull(cond) && TYPEOF(cond) != INTSXP) || TYPEOF(opts) != VECSXP)
     Rf_error("C_scdc_perm_counts: wrong argument types");
+  if (Rf_length(dim) != 2 || INTEGER(dim)[0] < 1 || INTEGER(dim)[1] < 1) Rf_error("dim must be c(n_cells, n_genes)");
   prob.n_cells = INTEGER(dim)[0];
   prob.n_genes = INTEGER(dim)[1];
+  if (Rf_xlength(p) != (R_xlen_t)prob.n_genes + 1) Rf_error("length(p) must be n_genes + 1");
+  if (Rf_xlength(i) != Rf_xlength(x) || Rf_xlength(i) < (R_xlen_t)INTEGER(p)[prob.n_genes])
+    Rf_error("i and x must have p[n_genes + 1] entries");
+  if (Rf_xlength(ct) != prob.n_cells || (!Rf_isNull(cond) && Rf_xlength(cond) != prob.n_cells))
+    Rf_error("ct and cond must have one entry per cell");
+  if (Rf_ncols(rows) != 3) Rf_error("rows must have 3 columns (LRI index, emitter code, receiver code)");
   prob.n_celltypes = (int32_t)opt_num(opts, "n_celltypes", 0);
   prob.n_conditions = Rf_isNull(cond) ? 1 : 2;
   prob.max_nL = (int32_t)opt_num(opts, "max_nL", 1);
@@ -83,13 +100,18 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   prob.row_recv = INTEGER(rows) + 2 * (size_t)prob.n_rows;
   prob.observed = REAL(observed);                    /* NA_real_ is a NaN: the engine treats it as NA */
 
-  opt.iterations = (int64_t)opt_num(opts, "iterations", 1000);
-  opt.seed = (uint64_t)opt_num(opts, "seed", 42);
-  opt.score_type = (int32_t)opt_num(opts, "score_type", SCDC_SCORE_GEOMETRIC);
-  opt.n_gpus = (int32_t)opt_num(opts, "n_gpus", 0);
-  opt.precision = SCDC_FP64_EXACT;
-  opt.return_distributions = (int32_t)opt_num(opts, "return_distributions", 0);
+  opt.iterations = (int64_t)opt_checked(opts, "iterations", 1000, 1, 2e9);
+  opt.seed = (uint64_t)opt_checked(opts, "seed", 42, 0, 9007199254740992.0 /* 2^53: exact in a double */);
+  opt.score_type = (int32_t)opt_checked(opts, "score_type", SCDC_SCORE_GEOMETRIC, 0, 1);
+  opt.n_gpus = (int32_t)opt_checked(opts, "n_gpus", 0, 0, 1024);
+  opt.precision = (int32_t)opt_checked(opts, "precision", SCDC_FP64_EXACT, 0, 1);
+  opt.rel_tol = opt_checked(opts, "rel_tol", 0, 0, 0.5);
+  opt.return_distributions = (int32_t)opt_checked(opts, "return_distributions", 0, 0, 1);
   SEXP pc = list_get(opts, "perm_cond"), pt = list_get(opts, "perm_ct");
+  const R_xlen_t n_lab = (R_xlen_t)opt.iterations * prob.n_cells;
+  if ((!Rf_isNull(pc) && (TYPEOF(pc) != RAWSXP || Rf_xlength(pc) != n_lab)) ||
+      (!Rf_isNull(pt) && (TYPEOF(pt) != RAWSXP || Rf_xlength(pt) != n_lab)))
+    Rf_error("perm_cond / perm_ct must be raw matrices n_cells x iterations");
   opt.perm_cond = Rf_isNull(pc) ? NULL : RAW(pc);    /* raw matrix N x iterations, column-major == [iterations][N] */
   opt.perm_ct = Rf_isNull(pt) ? NULL : RAW(pt);
   opt.interrupt = poll_user_interrupt;
@@ -99,6 +121,11 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   const size_t n = (size_t)prob.n_rows * ncols;
   uint64_t* counts = (uint64_t*)R_alloc(n ? n : 1, sizeof(uint64_t));   /* R-managed transient memory */
   res.counts = counts;
+  uint64_t* band = NULL;
+  if (opt.precision == SCDC_FP32_FAST) {
+    band = (uint64_t*)R_alloc(n ? n : 1, sizeof(uint64_t));
+    res.band_counts = band;
+  }
   SEXP dist = R_NilValue;
   if (opt.return_distributions) {
     const int ncd = prob.n_conditions == 2 ? 3 : 1;
@@ -131,6 +158,12 @@ SEXP C_scdc_perm_counts(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP ct, SEXP cond, SE
   }
   Rf_setAttrib(stats, R_NamesSymbol, snames);
   Rf_setAttrib(out, Rf_install("stats"), stats);
+  if (band) {
+    SEXP bm = PROTECT(Rf_allocMatrix(REALSXP, prob.n_rows, ncols));
+    ++nprot;
+    for (size_t k = 0; k < n; ++k) REAL(bm)[k] = (band[k] == SCDC_COUNT_NA) ? NA_REAL : (double)band[k];
+    Rf_setAttrib(out, Rf_install("band_counts"), bm);
+  }
   if (opt.return_distributions) Rf_setAttrib(out, Rf_install("distributions"), dist);
   UNPROTECT(nprot);
   return out;

@@ -12,6 +12,12 @@ typedef int Rboolean;
 #define INTSXP 13
 #define REALSXP 14
 #define STRSXP 16
+#define VECSXP 19
+#define RAWSXP 24
+typedef ptrdiff_t R_xlen_t;
+int R_IsNaN(double x);
+int R_IsNA(double x);
+#define ISNAN(x) ((x) != (x))
 extern SEXP R_NilValue, R_NamesSymbol;
 extern double R_NaReal;
 #define NA_REAL R_NaReal
@@ -24,6 +30,7 @@ SEXP STRING_ELT(SEXP x, ptrdiff_t i);
 void SET_STRING_ELT(SEXP x, ptrdiff_t i, SEXP v);
 SEXP VECTOR_ELT(SEXP x, ptrdiff_t i);
 int Rf_length(SEXP x);
+R_xlen_t Rf_xlength(SEXP x);
 int Rf_nrows(SEXP x);
 int Rf_ncols(SEXP x);
 Rboolean Rf_isNull(SEXP x);

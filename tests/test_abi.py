@@ -25,15 +25,33 @@ def test_library_exports_every_declared_symbol():
     assert sorted(syms) == sorted(_lib.EXPORTED)
     for s in syms:
         assert hasattr(lib, s), s
-    assert _lib.load().scdc_version().decode() == "0.1.0"
+    ver = re.search(r'SCDC_VERSION_STRING "([^"]+)"', open(os.path.join(ROOT, "include", "scdc.h")).read()).group(1)
+    assert _lib.load().scdc_version().decode() == ver
 
 
-def test_struct_layouts_match_header():
-    # sizes implied by include/scdc.h on LP64
-    assert C.sizeof(_lib.Problem) == 8 * 4 + 10 * 8
-    assert C.sizeof(_lib.Options) == 8 * 3 + 4 * 4 + 2 * 8 + 2 * 4 + 8 + 2 * 8
-    assert C.sizeof(_lib.Stats) == 9 * 8 + 3 * 8 + 2 * 4
-    assert C.sizeof(_lib.Result) == 3 * 8 + C.sizeof(_lib.Stats)
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors in _lib.py against the C compiler's view of include/scdc.h: size and offset of every field."""
+    import subprocess
+    structs = {"scdc_problem": _lib.Problem, "scdc_options": _lib.Options, "scdc_stats": _lib.Stats,
+               "scdc_result": _lib.Result, "scdc_observed": _lib.Observed}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "scdc.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, fname, val = ln.split()
+        got[(cname, fname)] = int(val)
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
 
 
 def _tiny_problem():

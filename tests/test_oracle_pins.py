@@ -102,6 +102,11 @@ def test_host_mirror_matches_oracle_observed_pass(liver_cases, oracle_cases):
                 checked += 1
         assert checked >= (9 if mode == "nocond" else 20)
         assert liver_cases[mode]["prob"].n_genes == (645 if mode == "cond" else 612)
+        if mode == "cond":   # per-subunit LOGFC columns (R/utils_cci.R:284-437): NA exactly where the subunit is absent
+            for name, col in (("L1", "LIGAND_1"), ("L2", "LIGAND_2"), ("R1", "RECEPTOR_1"), ("R3", "RECEPTOR_3")):
+                v = s[f"{name}_LOGFC"]
+                assert np.array_equal(v, s_o[f"{name}_LOGFC"], equal_nan=True)
+                assert np.array_equal(np.isnan(v), s_o[col] == "")
 
 
 @pytest.mark.parametrize("mode", ["cond", "nocond"])

@@ -241,17 +241,26 @@ def test_device_shuffles_are_uniform_differential(liver_cases):
     assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
 
 
-def test_in_library_multi_gpu_equals_single_gpu(liver_cases):
-    """scdc_perm_counts with n_gpus = 2: host thread per device, replicate ranges, ncclAllReduce of the counters."""
+@pytest.mark.parametrize("no_nccl", [0, 1])
+def test_in_library_multi_gpu_equals_single_gpu(liver_cases, no_nccl, monkeypatch):
+    """scdc_perm_counts with n_gpus = 2: the problem is uploaded once and broadcast over NVLink (ncclBroadcast, or peer
+    copies with SCDC_NO_NCCL=1), host thread per device, replicate ranges, ncclAllReduce of the counters (or peer copies +
+    adds)."""
     from scdiffcom_b200 import device_count
     if device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    monkeypatch.setenv("SCDC_NO_NCCL", str(no_nccl))
     for mode in ("cond", "nocond"):
         prob = liver_cases[mode]["prob"]
         one = perm_counts(prob, 1000, seed=3, n_gpus=1)
         two = perm_counts(prob, 1000, seed=3, n_gpus=2)
-        assert two["stats"]["n_gpus"] == 2
+        assert two["stats"]["n_gpus"] == 2 and two["stats"]["used_nccl"] == 1 - no_nccl
+        assert two["stats"]["p2p_bytes"] > prob.nnz * 12 and two["stats"]["h2d_bytes"] < 1.2 * one["stats"]["h2d_bytes"]
         assert np.array_equal(one["counts"], two["counts"], equal_nan=True)
+        f1 = perm_counts(prob, 1000, seed=3, n_gpus=1, precision="fp32_fast")
+        f2 = perm_counts(prob, 1000, seed=3, n_gpus=2, precision="fp32_fast")
+        assert np.array_equal(f1["counts"], f2["counts"], equal_nan=True)
+        assert np.array_equal(f1["band_counts"], f2["band_counts"], equal_nan=True)
         pcond, pct = helpers.reference_like_labels(prob, 300, 4)
         a = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=1)["counts"]
         b = perm_counts(prob, 300, perm_cond=pcond, perm_ct=pct, n_gpus=2)["counts"]
@@ -283,13 +292,28 @@ def test_observed_pass_on_gpu_and_one_resident_engine(liver, mode, score_type):
     bit (expression, detection rate, CCI_SCORE*, IS_CCI_EXPRESSED*: the reference's known-answer columns,
     tests/testthat/test-everything.R:377-490), and the same resident engine then runs the permutation test on the rows it
     found (scdc_set_rows) with the counts of the one-shot call."""
+    from oracle import oracle_np
     from scdiffcom_b200 import cci, preprocessing
     ai = helpers.liver_inputs(liver, mode, preprocessing)
     tmpl = cci.create_cci_template(ai)
     host = cci.run_simple_cci_analysis(ai, tmpl, score_type=score_type)
+    ai_o = helpers.liver_inputs(liver, mode, oracle_np)
+    want = oracle_np.run_simple_cci_analysis(ai_o, oracle_np.create_cci_template(ai_o), score_type=score_type)
     with Engine(cci.base_problem(ai)) as eng:
         dev = cci.run_simple_cci_analysis(ai, tmpl, score_type=score_type, engine=eng)
         assert set(dev) == set(host)
+        # against the ORACLE's table directly (string-keyed restatement of R/utils_cci.R:171-439), same row order
+        names = np.array(ai["cell_types"])
+        assert (names[dev["EMITTER_CODE"]] == want["EMITTER_CELLTYPE"]).all() and (ai["LRI"]["LRI"][dev["LRI_IDX"]] == want["LRI"]).all()
+        n_cmp = 0
+        for k, v in dev.items():
+            if k in want and np.asarray(v).dtype.kind in "fb":
+                if "LOGFC" in k:
+                    np.testing.assert_allclose(v, want[k], rtol=1e-15, atol=0, equal_nan=True)
+                else:
+                    assert np.array_equal(v, want[k], equal_nan=True), k
+                n_cmp += 1
+        assert n_cmp >= (9 if mode == "nocond" else 20)
         for k, v in host.items():
             if k in ("LOGFC", "LOGFC_ABS"):
                 np.testing.assert_allclose(dev[k], v, rtol=1e-15, atol=0)
