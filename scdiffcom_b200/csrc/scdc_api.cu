@@ -1017,16 +1017,24 @@ cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bp
 template <typename VT, int J>
 cudaError_t launch_scatter_j(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
                              void* M2, cudaStream_t s, const int* genes, int n_genes) {
+  // U = (value, label) slots per lane = how many entries ahead the label loads run; PAIR = two entries per dependent step.
+  // Few resident warps (large K) need the deepest pipeline and the pair mode.
+  const int warps_per_sm = pl.blocks_per_sm * pl.W;
   if constexpr (J == 1) {
-    // label prefetch depth: with few resident warps (large K) the L2 latency of the label loads needs a deeper pipeline
-    const int warps_per_sm = pl.blocks_per_sm * pl.W;
-    const int U = env_int("SCDC_U", (warps_per_sm <= 8) ? 16 : 8);
-    const int pair = env_int("SCDC_PAIR", (warps_per_sm <= 8) ? 1 : 0);
-    if (U == 16 && pair) return launch_scatter_u<VT, 1, 16, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-    if (U == 16) return launch_scatter_u<VT, 1, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-    if (pair) return launch_scatter_u<VT, 1, 8, true>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-    return launch_scatter_u<VT, 1, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    // registers per thread (ptxas): fp64 168 / 96 / 60 and fp32 132 / 80 / 48 for U = 32 / 16 / 8: the deepest pipeline
+    // that still lets the planned warps fit the 64 K registers of an SM
+    const bool f32 = sizeof(VT) == 4;
+    const int U = env_int("SCDC_U", warps_per_sm <= (f32 ? 15 : 12) ? 32 : (warps_per_sm <= (f32 ? 25 : 21) ? 16 : 8));
+    const int pair = env_int("SCDC_PAIR", (warps_per_sm <= 16) ? 1 : 0);
+#define SCDC_GO(UU, PP) return launch_scatter_u<VT, 1, UU, PP>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes)
+    if (U >= 32) { if (pair) SCDC_GO(32, true); SCDC_GO(32, false); }
+    if (U >= 16) { if (pair) SCDC_GO(16, true); SCDC_GO(16, false); }
+    if (pair) SCDC_GO(8, true);
+    SCDC_GO(8, false);
+#undef SCDC_GO
   } else {
+    const int U = env_int("SCDC_U", 16);
+    if (U >= 16) return launch_scatter_u<VT, J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
     return launch_scatter_u<VT, J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
   }
 }

@@ -979,20 +979,20 @@ __global__ void k_rec_to_float(size_t n, const uint4* __restrict__ in, uint2* __
 // M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
 // grid.x = nGa * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
 // ------------------------------------------------------------------------------------------------------------------
-// acc1 += v if sel != 0 else acc0 += v, written as two fused multiply-adds with a 1.0 / 0.0 selector: v * 1.0 + acc is
-// exactly acc + v (the product is exact, one rounding) and v * 0.0 + acc leaves acc unchanged, so the result is bit-identical
-// to the branchy form, in 5 instructions instead of the 7 (two adds + four selects + test) the compiler emits for it.
-__device__ __forceinline__ void sel_add(double& acc1, double& acc0, uint32_t sel, double v) {
-  // (two predicated add.f64 in inline PTX do not survive either: ptxas turns them into add + FSEL pairs)
-  const int hi1 = sel ? 0x3FF00000 : 0;
-  const double b1 = __hiloint2double(hi1, 0), b0 = __hiloint2double(hi1 ^ 0x3FF00000, 0);
-  acc1 = fma(v, b1, acc1);
-  acc0 = fma(v, b0, acc0);
-}
-__device__ __forceinline__ void sel_add(float& acc1, float& acc0, uint32_t sel, float v) {
-  const int w1 = sel ? 0x3F800000 : 0;
-  acc1 = fmaf(v, __int_as_float(w1), acc1);
-  acc0 = fmaf(v, __int_as_float(w1 ^ 0x3F800000), acc0);
+// acc1 += v if the condition bit is set, else acc0 += v, for the 8 replicates of a lane, branch-free and bit-identical to
+// the branchy form: vm = bit ? v : +0.0 (two FSEL on a predicate that R2P extracts for all 8 bits at once), acc1 += vm,
+// acc0 += (v - vm). v - vm is exactly 0 or v, and adding +0.0 leaves an accumulator unchanged, so each accumulator sees
+// exactly the additions of its own cells, in order. 5 issue slots per replicate (3 on the FP64 pipe); the multiplier form
+// of round 1 (two DFMA with a 1.0 / 0.0 selector) needed 6.7: ptxas spends a shift pair + two LOP3 + a register move on
+// every selector (ncu r2e: 72.6 instructions per entry x 256 replicates, ALU pipe 55 %, FP64 pipe 32 %).
+template <typename VT>
+__device__ __forceinline__ void sel_add8(VT (&acc1)[8], VT (&acc0)[8], uint32_t bits, VT v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const VT vm = ((bits >> j) & 1u) ? v : (VT)0;
+    acc1[j] += vm;
+    acc0[j] += (v - vm);
+  }
 }
 
 // Pass-1 condition bits, re-packed in place for k_pass1_cond. The label generators write, per cell, one 32-bit word per
@@ -1067,9 +1067,7 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
       auto accumulate = [&](const pack_t (&R)[U], const uint32_t (&B)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const VT v = Ent<VT>::value(R[u]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sel_add(a1[j], a0[j], B[u] & (1u << j), v);
+          sel_add8<VT>(a1, a0, B[u], Ent<VT>::value(R[u]));
         }
       };
       load_recs(R0, beg);
@@ -1123,8 +1121,12 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   const uint32_t ustride = (uint32_t)lab_stride;  // label address = 64-bit lane base + u32 cell * u32 stride: one IMAD.WIDE
   char* const accb = reinterpret_cast<char*>(acc);  // J = 1: accumulator row of label l starts at byte l * ROW
   // Matrix entries and the flushed means are streamed (evict-first) so that they do not push the labels out of L2.
-  // The labels of the NEXT group of U entries are loaded (L2 latency) while the CURRENT group is accumulated, and the
-  // entries two stages ahead are in flight from global memory: the read-modify-write chain never waits on a load.
+  // Software pipeline: U (value, label) slots live in registers. An entry is accumulated from its slot and the slot is
+  // refilled AT ONCE with the entry U positions further down the column (value from the staged broadcast, label from
+  // global memory / L2), so every label load has the accumulation of U - 1 other entries to complete in, with one set
+  // of U registers (round 1 kept a current and a next group: half the distance for the same registers; ncu r2a/r2e showed
+  // long-scoreboard stalls of 2.1 - 5.3 per issue with few resident warps). The entries two stages ahead are in flight
+  // from global memory: the read-modify-write chain never waits on a load.
   int cell_n = 0;
   VT v_n = 0;
   if (beg + lane < end) { cell_n = __ldcs(rowidx + beg + lane); v_n = __ldcs(values + beg + lane); }
@@ -1132,13 +1134,13 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
   cell_n = 0; v_n = 0;  // padding entries add +0.0 to cell 0's group: bit-neutral
   if (beg + 32 + lane < end) { cell_n = __ldcs(rowidx + beg + 32 + lane); v_n = __ldcs(values + beg + 32 + lane); }
   __syncwarp();
-  VT valN[U];
-  lab_t lbN[U];
+  VT val[U];
+  lab_t lb[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const pack_t en = stage[u];
-    valN[u] = Ent<VT>::value(en);
-    lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
+    val[u] = Ent<VT>::value(en);
+    lb[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
   }
   for (int s = 0; s < nst; ++s) {
     pack_t* cur_buf = stage + (s & 1) * 32;
@@ -1153,22 +1155,13 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
     __syncwarp();
 #pragma unroll
     for (int gq = 0; gq < 32 / U; ++gq) {
-      VT val[U];
-      lab_t lb[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) { val[u] = valN[u]; lb[u] = lbN[u]; }
+      // the slots hold entries [gq * U, gq * U + U) of stage s; their successors sit U entries further: in this stage's
+      // buffer, or (last group of the stage) at the head of the next stage's
       const pack_t* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const pack_t en = src[u];
-        valN[u] = Ent<VT>::value(en);
-        lbN[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
-      }
       if (PAIR && J == 1) {
         // Two entries per step: both accumulators are loaded before either add. If the two labels coincide the second
         // add continues from the first result, so the value stored last is ((acc + v1) + v2): the sequential sum, with a
-        // dependency chain of one shared-memory round trip per PAIR (matters when only ~7 warps are resident, K > 100;
-        // groups of four were measured no faster).
+        // dependency chain of one shared-memory round trip per PAIR (matters when few warps are resident).
 #pragma unroll
         for (int u = 0; u < U; u += 2) {
           VT* const p1 = reinterpret_cast<VT*>(accb + lb[u] * ROW);
@@ -1178,6 +1171,11 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
           const VT r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
           *p1 = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
           *p2 = r2;
+          const pack_t e1 = src[u], e2 = src[u + 1];
+          val[u] = Ent<VT>::value(e1);
+          lb[u] = load_labels<J>(labbase + (uint64_t)e1.x * ustride);
+          val[u + 1] = Ent<VT>::value(e2);
+          lb[u + 1] = load_labels<J>(labbase + (uint64_t)e2.x * ustride);
         }
       } else {
 #pragma unroll
@@ -1198,6 +1196,9 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
 #pragma unroll
             for (int j = 0; j < J; ++j) *row[j] = cur[j] + val[u];
           }
+          const pack_t en = src[u];
+          val[u] = Ent<VT>::value(en);
+          lb[u] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
         }
       }
     }
@@ -1548,25 +1549,26 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
   return r;
 }
 
-// x == +0.0, or 2^-930 <= x < 2^930: the inputs for which x * rsqrt.approx(x) is a 2^-20-accurate sqrt(x). One unsigned
-// compare of the high word: negative numbers, NaN, +inf, denormals and the far tails fall outside and take the exact path.
-__device__ __forceinline__ bool de_fast_range(double x) {
-  const uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
-  return (hi - 0x05D00000u) < 0x74400000u || (hi | lo) == 0u;  // exponent field in [1023 - 930, 1023 + 930)
-}
-
-// exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0. kslack = 2^-17 (8x the approximation's error), plus
-// 1.5 rel_tol with BAND, which widens the exactly-evaluated zone over the whole tolerance band: there bc also receives
-// the exact band_diff(sqrt(x1), sqrt(x0)) decision, and outside of it a comparison is provably not in the band.
+// exact value of (|sqrt(x1) - sqrt(x0)| >= aob) for aob >= 0, for ANY fp64 inputs, decided without an IEEE sqrt whenever the
+// approximation's error cannot change the outcome.
+//   s = x * rsqrt.approx(x + 1e-300): the added constant keeps the approximation finite at x = 0 (s = 0 = sqrt(0) exactly)
+//   and out of the flushed subnormal range; it perturbs s by less than 2^-60 relative for x >= 1e-260, and for smaller x
+//   both s and sqrt(x) are below 1e-130, so the error is below 1e-130 ABSOLUTE. rsqrt.approx.f64 is accurate to 2^-22 on
+//   normal inputs, so |s - sqrt(x)| <= 2^-20 sqrt(x) + 1e-130.
+//   slack = (s1 + s0) * kslack + 1e-120, kslack >= 2^-17: 8x the relative and 1e10x the absolute bound.
+//   Negative inputs, NaN and +inf make d NaN, so neither test passes and the IEEE path decides (as the reference would).
+// kslack = 2^-17, plus 1.5 rel_tol with BAND, which widens the exactly-evaluated zone over the whole tolerance band: there
+// bc also receives the exact band_diff(sqrt(x1), sqrt(x0)) decision, and outside of it a comparison is provably not in the
+// band. (Round 1 guarded the approximation with fmax(x, 1e-300) and an exponent-range test per operand: ~55 instructions
+// for this column alone; this form is 13 FP64 operations and two MUFU.)
 constexpr double kDeSlack = 7.62939453125e-06;  // 2^-17
 template <bool BAND>
 __device__ __forceinline__ bool de_exceeds(double x1, double x0, double aob, double kslack, double rt, uint32_t& bc) {
-  // fmax keeps the approximation finite at x = 0 (0 * finite = 0 = sqrt(0)); inputs in (0, 1e-300) are out of the fast range
-  const double s1 = x1 * rsqrt_approx(fmax(x1, 1e-300));
-  const double s0 = x0 * rsqrt_approx(fmax(x0, 1e-300));
-  const double d = fabs(s1 - s0), slack = (s1 + s0) * kslack;
+  const double s1 = x1 * rsqrt_approx(x1 + 1e-300);
+  const double s0 = x0 * rsqrt_approx(x0 + 1e-300);
+  const double d = fabs(s1 - s0), slack = fma(s1 + s0, kslack, 1e-120);
   const bool yes = d - slack > aob, no = d + slack < aob;
-  if (de_fast_range(x1) && de_fast_range(x0) && (yes || no)) return yes;
+  if (yes || no) return yes;
   const double e1 = sqrt(x1), e0 = sqrt(x0);
   if (BAND) bc += band_diff(e1, e0, aob, rt) ? 1u : 0u;
   return fabs(e1 - e0) >= aob;
@@ -1581,8 +1583,12 @@ __global__ void k_selftest_de(unsigned long long n, unsigned long long seed, uns
   philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x5eedu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
   const int kind = w[3] & 15;
   // log-uniform magnitudes; kind selects the exponent range
-  const double span = (kind < 10) ? 12.0 : (kind < 13 ? 300.0 : 40.0);
+  const double span = (kind < 9) ? 12.0 : (kind < 13 ? 300.0 : 40.0);
   double x0 = exp2((w[0] * (1.0 / 4294967296.0) - 0.5) * span), x1 = exp2((w[1] * (1.0 / 4294967296.0) - 0.5) * span);
+  if (kind == 9) {   // tiny and subnormal products, far tails: 2^-1074 .. 2^-850 and 2^850 .. 2^1023
+    x0 = exp2(-1074.0 + (w[0] * (1.0 / 4294967296.0)) * 224.0);
+    x1 = (w[3] & 16) ? exp2(850.0 + (w[1] * (1.0 / 4294967296.0)) * 173.0) : exp2(-1074.0 + (w[1] * (1.0 / 4294967296.0)) * 224.0);
+  }
   if (kind == 10) x0 = 0.0;
   if (kind == 11) x1 = x0;
   if (kind == 12) { x0 = 0.0; x1 = 0.0; }
@@ -1605,7 +1611,7 @@ __global__ void k_selftest_de(unsigned long long n, unsigned long long seed, uns
   if (want != got2 || (bc2 != 0) != want_band) atomicAdd(&out[0], 1ull);
   // was it decidable without the IEEE sqrt?
   const double s1 = (x1 == 0.0) ? 0.0 : x1 * rsqrt_approx(x1), s0 = (x0 == 0.0) ? 0.0 : x0 * rsqrt_approx(x0);
-  const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06;
+  const double d = fabs(s1 - s0), slack = (s1 + s0) * 7.62939453125e-06 + 1e-120;
   if (d - slack > aob || d + slack < aob) atomicAdd(&out[1], 1ull);
   // the approximation itself must stay well inside the band used by the filter
   if (x1 > 1e-280 && x1 < 1e280 && fabs(s1 - sqrt(x1)) > sqrt(x1) * 9.5367431640625e-07) atomicAdd(&out[2], 1ull);  // 2^-20
@@ -1814,21 +1820,26 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
       const double aob0 = fabs(ob[q][0]);
       const double o2a = ob[q][1] * ob[q][1], o2b = ob[q][2] * ob[q][2];
       uint32_t c0 = 0, c1 = 0, c2 = 0, b0 = 0, b1 = 0, b2 = 0;
+      // moving pointers (one add per replicate each) instead of p * Tp index arithmetic on every load
+      const float4* fa_p = reinterpret_cast<const float4*>(raw) + e_[q];
+      const float4* fb_p = reinterpret_cast<const float4*>(raw + (F32 ? sideStride : 0)) + r_[q];
+      const double2* pl = reinterpret_cast<const double2*>(raw);
+      const int pl2 = plane / 2;  // double2 per plane
+      const double2* d0_p = pl + e_[q];             // pass 1, emitter side
+      const double2* d1_p = pl + pl2 + r_[q];       // pass 1, receiver side
+      const double2* d2_p = pl + 2 * pl2 + e_[q];   // pass 2, emitter side
+      const double2* d3_p = pl + 3 * pl2 + r_[q];   // pass 2, receiver side
 #pragma unroll 2
       for (int p = 0; p < pmax; ++p) {
         double2 a1, a2, b1v, b2v;   // emitter / receiver minima: pass 1 (c1, c2), pass 2 (c1, c2)
         if (F32) {
-          const float4 fa = reinterpret_cast<const float4*>(raw)[p * Tp + e_[q]];
-          const float4 fb = reinterpret_cast<const float4*>(raw + sideStride)[p * Tp + r_[q]];
+          const float4 fa = *fa_p, fb = *fb_p;
+          fa_p += Tp; fb_p += Tp;
           a1 = make_double2((double)fa.x, (double)fa.y); a2 = make_double2((double)fa.z, (double)fa.w);
           b1v = make_double2((double)fb.x, (double)fb.y); b2v = make_double2((double)fb.z, (double)fb.w);
         } else {
-          const double2* pl = reinterpret_cast<const double2*>(raw);
-          const int pl2 = plane / 2;  // double2 per plane
-          a1 = pl[0 * pl2 + p * Tp + e_[q]];
-          b1v = pl[1 * pl2 + p * Tp + r_[q]];
-          a2 = pl[2 * pl2 + p * Tp + e_[q]];
-          b2v = pl[3 * pl2 + p * Tp + r_[q]];
+          a1 = *d0_p; b1v = *d1_p; a2 = *d2_p; b2v = *d3_p;
+          d0_p += Tp; d1_p += Tp; d2_p += Tp; d3_p += Tp;
         }
         if (A.score_type == 0) {
           c0 += de_exceeds<BAND>(a1.y * b1v.y, a1.x * b1v.x, aob0, kslack, rt, b0) ? 1u : 0u;
