@@ -224,6 +224,15 @@ int scdc_merge_pvalues(int64_t n_full, int64_t n_tested, const int64_t* tested_r
                        int64_t iterations, int32_t n_lri, int32_t max_nL, int32_t max_nR, const int32_t* sub_gene,
                        const int32_t* lri_idx, double* pvalues);
 
+/* ---- "next" item f4 (optional polish; north_star keeps filtering in R): stats::p.adjust(p, method = "BH") as the reference
+ * applies it to the permutation p-values in process_cci_raw (R/utils_filtering.R:216-235): NaN entries (NA) are left out
+ * of the ranking and stay NaN; out[i] = min(1, min over j with p_j >= p_i of n p_j / rank_j), n = number of non-NaN
+ * entries. `group` (may be NULL) = one integer key per entry: the adjustment is done separately inside every group (the
+ * reference's `by = temp_by`). Host-side helper; out may alias p. Counts themselves are resumable without any extra entry
+ * point: they are additive over replicate ranges (scdc_options.perm_offset), so a caller may add the counts of successive
+ * calls and divide by the total. */
+int scdc_bh_adjust(int64_t n, const double* p, const int32_t* group, double* out);
+
 /* Debug / test hook: the labels scdc_run would draw on the device for replicates [perm_offset, perm_offset + n),
  * row-major [n][N]. cond_out may be NULL in detection mode. */
 int scdc_draw_labels(scdc_handle* handle, uint64_t seed, int64_t perm_offset, int64_t n, uint8_t* cond_out,

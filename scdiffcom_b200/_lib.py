@@ -20,7 +20,7 @@ _ERRNAMES = {1: "SCDC_EINVAL", 2: "SCDC_ENOGPU", 3: "SCDC_ECUDA", 4: "SCDC_ENCCL
 # every symbol include/scdc.h declares (tests/test_abi.py checks header <-> library <-> this list)
 EXPORTED = (
     "scdc_perm_counts", "scdc_create", "scdc_run", "scdc_release", "scdc_group_means", "scdc_draw_labels",
-    "scdc_set_rows", "scdc_observed_pass", "scdc_trim", "scdc_cci_template", "scdc_merge_pvalues",
+    "scdc_set_rows", "scdc_observed_pass", "scdc_trim", "scdc_cci_template", "scdc_merge_pvalues", "scdc_bh_adjust",
     "scdc_selftest_de_filter", "scdc_last_error", "scdc_device_count", "scdc_version",
 )
 
@@ -107,6 +107,7 @@ def load():
                                        C.c_int32, C.POINTER(Observed)]
     lib.scdc_trim.argtypes = [C.c_int32]
     lib.scdc_cci_template.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 7
+    lib.scdc_bh_adjust.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scdc_merge_pvalues.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scdc_selftest_de_filter.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]

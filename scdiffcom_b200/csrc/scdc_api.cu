@@ -269,7 +269,6 @@ struct scdc_handle {
   DBuf<uint8_t> ct, cond;
   DBuf<uint32_t> expect;      // n(cell type, condition) as uint32 [K]
   DBuf<int> visit, ct_seg;     // K1 visit order (differential: cells stably sorted by cell type) and its segments
-  std::shared_ptr<std::vector<uint8_t>> obs_na;  // host: 1 where observed is NaN (shared by the clones of a multi-GPU call)
   // K3: rows grouped by LRI, split into block tasks; product thresholds for the one-sided geometric columns
   DBuf<int> task_lri, task_beg, task_end, srow;
   DBuf<double> thr, obs_sub;   // obs_sub: [L][T][nS] common observed subunit differences (factorised subunit columns)
@@ -280,6 +279,7 @@ struct scdc_handle {
   DBuf<uint8_t> lab2[2], up_cond, up_ct;
   DBuf<double> M1[2], M2[2], dist;   // group means are double-buffered: K3 of batch b overlaps K2 of batch b+1
   DBuf<int> flag, early_genes, keyfail;   // keyfail: overflow flag of the random-key label generator
+  DBuf<int> p1_counter;                   // work counter of the persistent pass-1 kernel
   DBuf<uint8_t> label_tmp;               // replicate-major labels of the random-key generator before re-layout
   double ms_upload = 0, h2d_bytes = 0;   // scdc_create: wall time and bytes copied host -> device
   size_t mem_total = 0;
@@ -532,23 +532,10 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
     int rc = install_active_genes(h, n_rows, row_lri);
     if (rc) return rc;
   }
-  CU(h->row_lri.upload(row_lri, n_rows, s));
-  CU(h->row_emit.upload(row_emit, n_rows, s));
-  CU(h->row_recv.upload(row_recv, n_rows, s));
-  CU(h->obs.upload(observed, (size_t)n_rows * h->ncols, s));
-  h->obs_na = std::make_shared<std::vector<uint8_t>>((size_t)n_rows * h->ncols);
-  std::vector<uint8_t>& obs_na = *h->obs_na;
-  const int n_thr = ((size_t)n_rows * h->ncols > (1u << 20)) ? 4 : 1;  // a few host threads on large tables
-  auto parallel = [&](auto&& fn) {
-    std::vector<std::thread> th;
-    for (int w = 1; w < n_thr; ++w) th.emplace_back([&fn, w]() { fn(w); });
-    fn(0);
-    for (auto& t : th) t.join();
-  };
-  parallel([&](int w) {
-    const size_t n = obs_na.size(), lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
-    for (size_t i = lo; i < hi; ++i) obs_na[i] = std::isnan(observed[i]) ? 1 : 0;
-  });
+  CU(upload_big(h->row_lri, row_lri, (size_t)n_rows, s));
+  CU(upload_big(h->row_emit, row_emit, (size_t)n_rows, s));
+  CU(upload_big(h->row_recv, row_recv, (size_t)n_rows, s));
+  CU(upload_big(h->obs, observed, (size_t)n_rows * h->ncols, s));   // NaN = NA: marked in the counters on the device (k_mark_na)
   // K3 work list: rows stably sorted by LRI (counting sort), each LRI cut into slices of score_threads * kScoreRPT rows
   std::vector<int> srow(n_rows), t_lri, t_beg, t_end;
   {
@@ -578,30 +565,23 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
         (size_t)n_rows * C, h->obs.p + (C == 2 ? (size_t)n_rows : 0), h->thr.p);
     CU(cudaGetLastError());
   }
-  std::vector<double> obs_sub;
   h->fact_ok = false;
-  if (C == 2) {
+  bool fact_pending = false;
+  if (C == 2 && n_rows > 0 && !env_int("SCDC_NO_FACT", 0)) {
     // The subunit columns of a row depend only on (LRI, emitter) / (LRI, receiver). If the observed subunit
     // differences agree bitwise across the rows sharing such a pair (true for tables built by the reference, where they
-    // are joins of the same group means), K3 counts them once per (cell type, subunit).
+    // are joins of the same group means), K3 counts them once per (cell type, subunit). Table and check on the device.
     const size_t n_tab = (size_t)h->L * T * h->nS;
-    obs_sub.assign(n_tab, std::nan(""));
-    std::vector<uint8_t> seen(n_tab, 0);
-    std::atomic<bool> ok{true};
-    parallel([&](int w) {  // thread w owns the LRIs with lri % n_thr == w: disjoint table entries, no races
-      for (int r = 0; r < n_rows && ok.load(std::memory_order_relaxed); ++r) {
-        if (row_lri[r] % n_thr != w) continue;
-        for (int sidx = 0; sidx < h->nS; ++sidx) {
-          const int ctx = (sidx < h->nL) ? row_emit[r] : row_recv[r];
-          const size_t k = ((size_t)row_lri[r] * T + ctx) * h->nS + sidx;
-          const double v = observed[(size_t)(3 + sidx) * n_rows + r];
-          if (!seen[k]) { seen[k] = 1; obs_sub[k] = v; }
-          else if (memcmp(&obs_sub[k], &v, sizeof v) != 0 && !(std::isnan(obs_sub[k]) && std::isnan(v))) { ok = false; break; }
-        }
-      }
-    });
-    h->fact_ok = ok.load() && !env_int("SCDC_NO_FACT", 0);
-    if (h->fact_ok) CU(h->obs_sub.upload(obs_sub.data(), n_tab, s));
+    CU(h->obs_sub.alloc(n_tab));
+    CU(h->flag.ensure(1));
+    CU(cudaMemsetAsync(h->obs_sub.p, 0xFF, n_tab * sizeof(double), s));  // all-ones = NaN: unused / absent
+    CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
+    const unsigned nb = (unsigned)((n_rows + 255) / 256);
+    scdc::k_fact_fill<<<nb, 256, 0, s>>>(n_rows, T, h->nL, h->nS, h->row_lri.p, h->row_emit.p, h->row_recv.p, h->obs.p, h->obs_sub.p);
+    scdc::k_fact_check<<<nb, 256, 0, s>>>(n_rows, T, h->nL, h->nS, h->row_lri.p, h->row_emit.p, h->row_recv.p, h->obs.p,
+                                          h->obs_sub.p, h->flag.p);
+    CU(cudaGetLastError());
+    fact_pending = true;
   }
   CU(h->srow.upload(srow.data(), srow.size(), s));
   CU(h->task_lri.upload(t_lri.data(), t_lri.size(), s));
@@ -609,6 +589,11 @@ static int install_rows(scdc_handle* h, int n_rows, const int32_t* row_lri, cons
   CU(h->task_end.upload(t_end.data(), t_end.size(), s));
   pt.lap("rows: enqueue rest");
   CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
+  if (fact_pending) {
+    int mismatch = 1;
+    CU(cudaMemcpy(&mismatch, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    h->fact_ok = mismatch == 0;
+  }
   if (up) {
     cudaEvent_t done;
     CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -820,7 +805,9 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       if (rc) return rc;
       rc = launch_early_scatter(h.get(), o_hint);
       if (rc) return rc;
-      if (h->pre.k2_done) s_up = h->stream_score;
+      // the rows' uploads and small kernels go to the HIGH-priority label stream (idle by now): on a low-priority stream
+      // their blocks starved behind the scatter's 24 k blocks and create waited ~350 ms for them (SCDC_TIMING, config 5)
+      if (h->pre.k2_done) s_up = h->stream_labels;
     }
     if (C == 2) {
       // pass-1 copy of the matrix (inside each gene column, entries stably sorted by cell type), built on the device from
@@ -1021,10 +1008,10 @@ cudaError_t launch_scatter_j(const scdc_handle* h, const ScatterPlan& pl, int Bp
   // Few resident warps (large K) need the deepest pipeline and the pair mode.
   const int warps_per_sm = pl.blocks_per_sm * pl.W;
   if constexpr (J == 1) {
-    // registers per thread (ptxas): fp64 168 / 96 / 60 and fp32 132 / 80 / 48 for U = 32 / 16 / 8: the deepest pipeline
-    // that still lets the planned warps fit the 64 K registers of an SM
-    const bool f32 = sizeof(VT) == 4;
-    const int U = env_int("SCDC_U", warps_per_sm <= (f32 ? 15 : 12) ? 32 : (warps_per_sm <= (f32 ? 25 : 21) ? 16 : 8));
+    // registers per thread (ptxas): fp64 168 / 96 / 60 and fp32 132 / 80 / 48 for U = 32 / 16 / 8. Measured on config 5
+    // (K = 120): fp64, 7 warps / SM: U = 32 343 ms vs U = 16 430 ms per 2560 replicates; fp32, 14 warps / SM: U = 16
+    // 486 ms per 6400 vs U = 32 695 ms (U = 32 halves the resident warps there).
+    const int U = env_int("SCDC_U", warps_per_sm <= 8 ? 32 : (warps_per_sm <= 24 ? 16 : 8));
     const int pair = env_int("SCDC_PAIR", (warps_per_sm <= 16) ? 1 : 0);
 #define SCDC_GO(UU, PP) return launch_scatter_u<VT, 1, UU, PP>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes)
     if (U >= 32) { if (pair) SCDC_GO(32, true); SCDC_GO(32, false); }
@@ -1088,12 +1075,17 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
     // equal batches: the reduction always runs whole batches, so n batches of the smallest multiple of q that covers
     // iterations / n waste at most q - 1 replicates per batch (10 000 -> 1 x 10 112 instead of 3 x 4096); among the batch
     // counts that fit the memory budget (and up to twice the minimum) take the one that pads least
+    // ... where "pads" counts what the scatter really runs: whole blocks of W warps x 32 J replicates (config 5, 12 500
+    // replicates: 5 x 2560 would run 5 x 84 chunks for 80 useful ones each, 7 x 1792 runs 7 x 56 full ones)
     const long long n_min = (o->iterations + B - 1) / B;
     long long best_B = 0, best_total = 0;
-    for (long long n = n_min; n <= 2 * n_min; ++n) {
+    for (long long n = n_min; n <= 3 * n_min + 1; ++n) {
       const long long Bn = (((o->iterations + n - 1) / n + q - 1) / q) * q;
       if (Bn > B) continue;
-      if (!best_B || n * Bn < best_total) { best_B = Bn; best_total = n * Bn; }
+      const ScatterPlan pn = plan_scatter(h, (int)Bn, o->precision == SCDC_FP32_FAST);
+      const long long slice = 32LL * pn.J * pn.W;
+      const long long total = n * (((Bn + slice - 1) / slice) * slice);
+      if (!best_B || total < best_total) { best_B = Bn; best_total = total; }
     }
     if (best_B) B = best_B;
   } else {
@@ -1293,6 +1285,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     CU(h->M2[i].ensure(msz));
   }
   CU(h->counts.ensure((size_t)R * h->ncols + 1));
+  if (C == 2) CU(h->p1_counter.ensure(1));
   if (f32) {
     CU(h->band.ensure((size_t)R * h->ncols + 1));
     int rc = ensure_f32_values(h, h->stream, false);
@@ -1473,13 +1466,24 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     // then launched after the scatter on a second stream, in small blocks that fit into the registers / shared memory the
     // scatter leaves free on every SM, and joined before K3.
     const int ov1 = (C == 2) ? env_int("SCDC_OVERLAP_PASS1", 1) : 0;
-    auto launch_pass1 = [&](cudaStream_t sp, int W) -> cudaError_t {
+    // persistent = a small grid whose warps pull (gene, chunk) items from a counter; used when pass 1 runs next to the scatter
+    auto launch_pass1 = [&](cudaStream_t sp, int W, bool persistent) -> cudaError_t {
       const int nWC = B / 256;
       const long long tasks = (long long)h->n_active * nWC;
-      const unsigned grid1 = (unsigned)((tasks + W - 1) / W);
+      unsigned grid1 = (unsigned)((tasks + W - 1) / W);
+      int* counter = nullptr;
+      if (persistent) {
+        // blocks per SM: one next to the fp64 scatter (168 registers per thread at U = 32), two next to the fp32 one
+        // (measured, config 5 / config 3: fp64 1895 vs 2206 / 279 vs 286 ms of reduction per step, fp32 1219 vs 1158 / 162 vs 142)
+        grid1 = (unsigned)std::min<long long>(grid1, (long long)h->num_sms * std::max(1, env_int("SCDC_P1_BLOCKS", f32 ? 2 : 1)));
+        counter = h->p1_counter.p;
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), sp);
+        if (e != cudaSuccess) return e;
+      }
       const int U1 = env_int("SCDC_U1", 4);  // records per pipeline stage
       auto go = [&](auto kern, auto* rec, auto* M1t) {
-        kern<<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p, M1t);
+        kern<<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p, M1t,
+                                       counter);
       };
       if (f32) {
         if (U1 == 2) go(scdc::k_pass1_cond<float, 2>, h->rec_sf.p, static_cast<float*>(M1b));
@@ -1491,10 +1495,20 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       return cudaGetLastError();
     };
     if (C == 2 && !ov1) {
-      CU(launch_pass1(s, 4));
+      CU(launch_pass1(s, 4, false));
       ++launches; ++reduce_launches;
     }
-    if (C == 2 && ov1) CU(cudaEventRecord(ov_fork, s));  // labels, means buffers and everything before are ready
+    if (C == 2 && ov1) {
+      // Pass 1 (FP64 / issue-slot bound, registers only) runs NEXT TO the pass-2 scatter (shared-memory-pipe bound): its
+      // persistent grid of a block per SM is launched first, on a high-priority stream, so that its blocks are resident on
+      // every SM before the scatter's blocks fill the rest; joined before K3.
+      cudaStream_t sp1 = pipelined ? h->stream_score : h->stream_labels;  // (the label stream draws ahead when pipelined)
+      CU(cudaEventRecord(ov_fork, s));  // labels, means buffers and everything before are ready
+      CU(cudaStreamWaitEvent(sp1, ov_fork, 0));
+      CU(launch_pass1(sp1, env_int("SCDC_W1", 4), env_int("SCDC_P1_PERSISTENT", 1) != 0));
+      CU(cudaEventRecord(ov_join, sp1));
+      ++launches; ++reduce_launches;
+    }
     if (early_k2 && done == 0) {
       launches += h->pre.k2_launches;  // batch 0 was reduced behind the matrix upload (upload_matrix_with_early_reduction)
       reduce_launches += h->pre.k2_launches;
@@ -1502,13 +1516,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(launch_scatter(h, pl, B, lab2_b, B, M2b, s));
       ++launches; ++reduce_launches;
     }
-    if (C == 2 && ov1) {
-      CU(cudaStreamWaitEvent(h->stream_score, ov_fork, 0));
-      CU(launch_pass1(h->stream_score, env_int("SCDC_W1", 4)));
-      CU(cudaEventRecord(ov_join, h->stream_score));
-      CU(cudaStreamWaitEvent(s, ov_join, 0));
-      ++launches; ++reduce_launches;
-    }
+    if (C == 2 && ov1) CU(cudaStreamWaitEvent(s, ov_join, 0));
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
@@ -1546,14 +1554,29 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
         D.sub_gene = h->sub_gene.p; D.row_emit = h->row_emit.p; D.row_recv = h->row_recv.p; D.obs = h->obs.p;
         D.thr = h->thr.p; D.obs_sub = h->obs_sub.p; D.M1 = M1b; D.M2 = M2b; D.counts = h->counts.p;
         D.band = h->band.p; D.rel_tol = rel_tol;
-        auto go = [&](auto kern) -> cudaError_t {
-          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto go = [&](auto kern, size_t smem_k) -> cudaError_t {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k);
           if (e != cudaSuccess) return e;
-          kern<<<h->n_tasks, h->score_threads, smem, sS>>>(D);
+          kern<<<h->n_tasks, h->score_threads, smem_k, sS>>>(D);
           return cudaGetLastError();
         };
-        if (f32) CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, float, true>) : go(scdc::k_score_diff<kScoreRPT, false, float, true>));
-        else CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, double, false>) : go(scdc::k_score_diff<kScoreRPT, false, double, false>));
+        if (fact && env_int("SCDC_SCORE_BULK", 1)) {
+          // tiles in the means' natural layout, filled by cp.async.bulk + mbarrier (k_score_diff_bulk): rows padded to
+          // P + 2 (fp64) / P + 4 (fp32) elements, two buffers of 8 planes x T rows
+          const size_t es = f32 ? 4 : 8;
+          const int pad = f32 ? 4 : 2;
+          int Pb = 32;
+          while (Pb > 4 && 2 * 8 * (size_t)T * (Pb + pad) * es + tail > smem_target) Pb >>= 1;
+          Pb = env_int("SCDC_SCORE_P", Pb);
+          D.P = Pb;
+          const size_t smem_b = ((2 * 8 * (size_t)T * (Pb + pad) * es + 7) / 8) * 8 + tail;
+          if (f32) CU(go(scdc::k_score_diff_bulk<kScoreRPT, float, true>, smem_b));
+          else CU(go(scdc::k_score_diff_bulk<kScoreRPT, double, false>, smem_b));
+        } else if (f32) {
+          CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, float, true>, smem) : go(scdc::k_score_diff<kScoreRPT, false, float, true>, smem));
+        } else {
+          CU(fact ? go(scdc::k_score_diff<kScoreRPT, true, double, false>, smem) : go(scdc::k_score_diff<kScoreRPT, false, double, false>, smem));
+        }
       } else {
         scdc::ScoreDetArgs A;
         A.G = G; A.T = T; A.Tp = Tp; A.nL = h->nL; A.nS = h->nS; A.score_type = o->score_type;
@@ -1661,19 +1684,22 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   return SCDC_OK;
 }
 
-// uint32 device counters -> the caller's uint64 array with the NA marks (a few host threads on large tables)
-int counts_to_host(const scdc_handle* h, const uint32_t* dev, uint64_t* out) {
+// uint32 device counters -> the caller's uint64 array. The (row, column) entries whose observed value is NA are first
+// marked on the device (k_mark_na writes 0xFFFFFFFF, no counter can reach it) and become SCDC_COUNT_NA here.
+int counts_to_host(const scdc_handle* h, uint32_t* dev, uint64_t* out, cudaStream_t s) {
   const size_t n = (size_t)h->R * h->ncols;
   if (!n) return SCDC_OK;
   std::unique_ptr<uint32_t[]> raw32(new (std::nothrow) uint32_t[n]);
   if (!raw32) return fail(SCDC_ENOMEM, "host allocation failed");
-  CU(cudaMemcpy(raw32.get(), dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  scdc::k_mark_na<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->obs.p, dev);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(raw32.get(), dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   g_d2h_bytes += (double)n * sizeof(uint32_t);
-  const std::vector<uint8_t>& na = *h->obs_na;
   const int n_thr = (n > (1u << 20)) ? 4 : 1;
   auto body = [&](int w) {
     const size_t lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
-    for (size_t i = lo; i < hi; ++i) out[i] = na[i] ? SCDC_COUNT_NA : (uint64_t)raw32[i];
+    for (size_t i = lo; i < hi; ++i) out[i] = (raw32[i] == 0xFFFFFFFFu) ? SCDC_COUNT_NA : (uint64_t)raw32[i];
   };
   std::vector<std::thread> th;
   try {
@@ -1783,7 +1809,6 @@ int clone_handles(std::vector<scdc_handle*>& hs, const std::vector<int>& devs, s
     if (rc) return rc;
     h->N = h0->N; h->G = h0->G; h->T = h0->T; h->C = h0->C; h->L = h0->L; h->R = h0->R; h->nL = h0->nL; h->nR = h0->nR;
     h->K = h0->K; h->ncols = h0->ncols; h->nS = h0->nS; h->nnz = h0->nnz;
-    h->obs_na = h0->obs_na;
     h->fact_ok = h0->fact_ok; h->n_tasks = h0->n_tasks; h->score_threads = h0->score_threads;
     h->sub_gene_h = h0->sub_gene_h; h->gene_nnz_h = h0->gene_nnz_h;
     h->max_nt = h0->max_nt; h->max_nc = h0->max_nc; h->n_active = h0->n_active; h->nnz_active = h0->nnz_active;
@@ -1858,17 +1883,18 @@ int scdc_run(scdc_handle* h, const scdc_options* o, scdc_result* res) {
     CU(cudaStreamSynchronize(s));
     res->stats.kernel_launches += 1;
   }
-  if (res->counts) {
-    rc = counts_to_host(h, h->counts.p, res->counts);
+  // (the widened copies above were taken before the NA marks go into the uint32 counters)
+  if (res->counts || res->band_counts) {
+    rc = counts_to_host(h, h->counts.p, res->counts ? res->counts : res->band_counts, s);
     if (rc) return rc;
   }
   if (res->band_counts) {
     if (f32) {
-      rc = counts_to_host(h, h->band.p, res->band_counts);
+      rc = counts_to_host(h, h->band.p, res->band_counts, s);
       if (rc) return rc;
-    } else {
-      const std::vector<uint8_t>& na = *h->obs_na;
-      for (size_t i = 0; i < n; ++i) res->band_counts[i] = na[i] ? SCDC_COUNT_NA : 0;
+    } else {  // nothing is approximated in fp64: zero, with the NA pattern of the counts
+      const uint64_t* src = res->counts ? res->counts : res->band_counts;
+      for (size_t i = 0; i < n; ++i) res->band_counts[i] = (src[i] == SCDC_COUNT_NA) ? SCDC_COUNT_NA : 0;
     }
   }
   res->stats.ms_merge = now_ms() - t1;
@@ -2058,12 +2084,11 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   }
   if (!bad) {
     cudaSetDevice(hs[0]->device);
-    if (counts_to_host(hs[0], hs[0]->counts.p, res->counts)) bad = 3;
+    if (counts_to_host(hs[0], hs[0]->counts.p, res->counts, hs[0]->stream)) bad = 3;
     if (!bad && res->band_counts) {
-      if (f32) { if (counts_to_host(hs[0], hs[0]->band.p, res->band_counts)) bad = 3; }
+      if (f32) { if (counts_to_host(hs[0], hs[0]->band.p, res->band_counts, hs[0]->stream)) bad = 3; }
       else {
-        const std::vector<uint8_t>& na = *hs[0]->obs_na;
-        for (size_t i = 0; i < n; ++i) res->band_counts[i] = na[i] ? SCDC_COUNT_NA : 0;
+        for (size_t i = 0; i < n; ++i) res->band_counts[i] = (res->counts[i] == SCDC_COUNT_NA) ? SCDC_COUNT_NA : 0;
       }
     }
   }
@@ -2298,6 +2323,41 @@ int scdc_merge_pvalues(int64_t n_full, int64_t n_tested, const int64_t* tested_r
       for (int64_t k = lo; k < hi; ++k) col[tested_rows[k]] = (cnt[k] == SCDC_COUNT_NA) ? nan : (double)cnt[k] / it;
     }
   });
+  return SCDC_OK;
+}
+
+int scdc_bh_adjust(int64_t n, const double* p, const int32_t* group, double* out) {
+  if (n < 0 || (n > 0 && (!p || !out))) return fail(SCDC_EINVAL, "bad p-value arrays");
+  try {
+    std::vector<int64_t> idx;
+    idx.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i)
+      if (!std::isnan(p[i])) idx.push_back(i);
+    // by group, then by DEcreasing p (stable: ties keep their order, as order(p, decreasing = TRUE) does)
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) {
+      if (group && group[a] != group[b]) return group[a] < group[b];
+      return p[a] > p[b];
+    });
+    std::vector<double> adj(idx.size());
+    for (size_t b = 0; b < idx.size();) {
+      size_t e = b;
+      while (e < idx.size() && (!group || group[idx[e]] == group[idx[b]])) ++e;
+      const double m = (double)(e - b);
+      double run = INFINITY;  // cummin(n / (n:1) * p[o]) over decreasing p
+      for (size_t k = b; k < e; ++k) {
+        const double rank = m - (double)(k - b);  // n, n - 1, ..., 1
+        const double v = m / rank * p[idx[k]];
+        run = std::min(run, v);
+        adj[k] = std::min(1.0, run);
+      }
+      b = e;
+    }
+    for (int64_t i = 0; i < n; ++i)
+      if (std::isnan(p[i])) out[i] = p[i];
+    for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = adj[k];
+  } catch (const std::bad_alloc&) {
+    return fail(SCDC_ENOMEM, "host allocation failed");
+  }
   return SCDC_OK;
 }
 

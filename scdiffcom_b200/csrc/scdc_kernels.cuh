@@ -1030,24 +1030,35 @@ __global__ void k_bits_transpose8(size_t n_groups, uint32_t* __restrict__ bits) 
 // memory at K > 100 but few registers and issue slots; this kernel needs only registers, FP64 and issue slots).
 // The loads are software-pipelined three groups deep (records of group i + 2 and bits of group i + 1 in flight while
 // group i is accumulated). Padding records are (cell 0, +0.0): bit-neutral.
-// bits: [cell][Bb] bytes with Bb = B / 8 (one batch block). grid.x = ceil(nGa * (B / 256) / W), block = 32 * W.
+// bits: [cell][Bb] bytes with Bb = B / 8 (one batch block). Work item = (active gene, 256-replicate warp chunk), heavy genes
+// first. work_counter == nullptr: item = global warp index, grid.x = ceil(nGa * (B / 256) / W). work_counter != nullptr
+// (zeroed before the launch): PERSISTENT form — a small grid (a block or two per SM) whose warps pull items from the
+// counter until none is left. Launched before the pass-2 scatter, its few blocks sit on every SM for the whole batch and
+// the scatter's blocks fill the rest of the SM (its shared memory, most of its registers): the two kernels run side by side
+// by construction instead of at the block scheduler's discretion. block = 32 * W.
 template <typename VT, int U>
 __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
                                                     const typename Ent<VT>::pack* __restrict__ rec,
                                                     const uint8_t* __restrict__ bits, int Bb,
                                                     const double* __restrict__ ngroup, const int* __restrict__ gene_order,
-                                                    VT* __restrict__ M1) {
+                                                    VT* __restrict__ M1, int* __restrict__ work_counter) {
   typedef typename Ent<VT>::pack pack_t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-  const long long task = (long long)blockIdx.x * W + warp;
-  if (task >= (long long)nGa * nWC) return;  // nGa active genes (gene_order), G = layout stride of M1
-  const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
+  const long long n_tasks = (long long)nGa * nWC;  // nGa active genes (gene_order), G = layout stride of M1
   const int K = 2 * T;
+  const pack_t zero = Ent<VT>::make(0, (VT)0);
+  for (long long task = (long long)blockIdx.x * W + warp;;) {
+  if (work_counter) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(work_counter, 1);
+    task = __shfl_sync(0xffffffffu, t, 0);
+  }
+  if (task >= n_tasks) return;
+  const int g = gene_order[(int)(task / nWC)], wc = (int)(task % nWC);
   const int* sp = segptr + (size_t)g * (T + 1);
   const uint8_t* bitbase = bits + wc * 32 + lane;  // + cell * Bb: the byte with this lane's 8 condition bits
   asm("" : "+l"(bitbase));
   const uint32_t ubb = (uint32_t)Bb;  // the address is one IMAD.WIDE (u32 cell x u32 stride + 64-bit lane base)
-  const pack_t zero = Ent<VT>::make(0, (VT)0);
   for (int t = 0; t < T; ++t) {
     const int beg = sp[t], end = sp[t + 1];
     VT a0[8], a1[8];
@@ -1087,6 +1098,8 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
       __stcs(&M1[base + (size_t)(T + t) * 32], a1[j] / n1);
     }
   }
+  if (!work_counter) return;
+  }  // next work item
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1907,6 +1920,251 @@ __global__ void __launch_bounds__(256, 2) k_score_diff(ScoreDiffArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K3, differential mode, tiles filled by the TMA unit (cp.async.bulk + mbarrier): the production kernel whenever the
+// subunit columns factorise (FACT). The tile keeps the means' NATURAL layout: for every (side, pass, cond) plane and cell
+// type, the P consecutive replicates of the tile are one contiguous piece (P x sizeof(MT) bytes, 16-byte aligned) of the
+// 256-byte row [gene][k][32 lanes] in global memory, so ONE bulk copy issued by ONE thread moves it: 8 T copies per tile
+// instead of 8 T P eight-byte LDGSTS (the cp.async kernel above spends ~9 % of its instructions on them at T = 60: ncu
+// r2e source page), completion is signalled on an mbarrier (transaction bytes) instead of per-thread wait_group +
+// __syncthreads. Shared-memory rows are padded to PP = P + 2 (fp64) / P + 4 (fp32) elements: the row stride in 16-byte chunks
+// is odd, so the rows of a warp (consecutive receivers) read their 16-byte vectors — 2 (fp64) / 4 (fp32) replicates of one
+// plane — from distinct bank groups. Everything else (fix-up votes of the FACT columns, exact DE decision, product
+// thresholds, band counters) is the arithmetic of k_score_diff.
+// shared memory: RAW[2 buffers][8 planes = side * 4 + pass * 2 + cond][T][PP] of MT, then SO / CNT (/ BND) as in k_score_diff.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+template <int RPT, typename MT, bool BAND>
+__global__ void __launch_bounds__(256, 2) k_score_diff_bulk(ScoreDiffArgs A) {
+  extern __shared__ __align__(16) double sm_d[];
+  constexpr bool F32 = sizeof(MT) == 4;
+  constexpr int V = F32 ? 4 : 2;               // replicates per 16-byte vector
+  const MT* const M1 = reinterpret_cast<const MT*>(A.M1);
+  const MT* const M2 = reinterpret_cast<const MT*>(A.M2);
+  __shared__ int s_gs[8];
+  __shared__ int s_extra;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  const int l = A.task_lri[blockIdx.x], rb = A.task_beg[blockIdx.x], re = A.task_end[blockIdx.x];
+  const int T = A.T, P = A.P, K = A.K, nL = A.nL, nR = A.nR, nS = nL + nR;
+  const int PP = P + (F32 ? 4 : 2);
+  const double rt = A.rel_tol;
+  const double kslack = kDeSlack + (BAND ? 1.5 * rt : 0.0);
+  if (tid < 8) s_gs[tid] = (tid < nS) ? A.sub_gene[l * nS + tid] : -1;
+  if (tid == 0) {
+    int extra = 0;
+    for (int s = 0; s < nS; ++s)
+      if (s != 0 && s != nL && A.sub_gene[l * nS + s] >= 0) extra = 1;
+    s_extra = extra;
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  int e_[RPT], r_[RPT], rid[RPT];
+  double ob[RPT][3], th[RPT][2];
+  uint32_t cnt[RPT][3], bnd[RPT][BAND ? 3 : 1];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int pos = rb + tid + q * nthr;
+    rid[q] = (pos < re) ? A.srow[pos] : -1;
+    e_[q] = r_[q] = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ob[q][c] = 0.0; cnt[q][c] = 0; }
+#pragma unroll
+    for (int c = 0; c < (BAND ? 3 : 1); ++c) bnd[q][c] = 0;
+    th[q][0] = th[q][1] = 0.0;
+    if (rid[q] >= 0) {
+      e_[q] = A.row_emit[rid[q]];
+      r_[q] = A.row_recv[rid[q]];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ob[q][c] = A.obs[(size_t)c * A.R + rid[q]];
+      th[q][0] = A.thr[rid[q]];
+      th[q][1] = A.thr[(size_t)A.R + rid[q]];
+    }
+  }
+  const int planeSz = T * PP;                   // elements of one plane
+  const int rawSize = 8 * planeSz;              // elements of one RAW buffer
+  MT* const rawbase = reinterpret_cast<MT*>(sm_d);
+  double* const tail = sm_d + (2 * (size_t)rawSize * sizeof(MT) + 7) / 8;
+  double* const SO = tail;
+  uint32_t* const CNT = reinterpret_cast<uint32_t*>(tail + T * nS);
+  uint32_t* const BND = CNT + T * nS;
+  for (int i = tid; i < T * nS; i += nthr) {
+    SO[i] = fabs(A.obs_sub[(size_t)l * T * nS + i]);  // NaN (absent / unused): never exceeded, never in the band
+    CNT[i] = 0;
+    if (BAND) BND[i] = 0;
+  }
+  const int n_tiles = (A.n_valid + P - 1) / P;
+  __syncthreads();
+  const int g_first[2] = {s_gs[0], s_gs[nL]};
+  const bool has_extra = s_extra != 0;
+  const int lgP = 31 - __clz(P);
+  const int p_t = tid & (P - 1), ct0 = tid >> lgP, ctstep = nthr >> lgP;
+  const int n_ct_iter = (T + ctstep - 1) / ctstep;   // uniform trip count: the fix-up pass votes with full-warp ballots
+  const uint32_t gmask = ((P >= 32) ? 0xffffffffu : ((1u << P) - 1u)) << (lane & ~(P - 1) & 31);
+  const bool gleader = (lane & (P - 1) & 31) == 0;
+  const unsigned row_bytes = (unsigned)(P * sizeof(MT));
+  // tile t -> buffer t & 1: thread 0 arms the buffer's mbarrier with the tile's bytes, the threads share the 8 T copies
+  auto issue = [&](int t) {
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    MT* dst0 = rawbase + (size_t)(t & 1) * rawSize;
+    uint64_t* bar = &s_bar[t & 1];
+    if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)(8 * T) * row_bytes);
+    for (int i = tid; i < 8 * T; i += nthr) {
+      const int q = i / T, ct = i - q * T, side = q >> 2, k = q & 3;
+      const MT* src = ((k >> 1) ? M2 : M1) + (((size_t)ch * A.G + g_first[side]) * K + (k & 1) * T + ct) * 32 + lane0;
+      bulk_g2s(dst0 + (size_t)q * planeSz + ct * PP, src, row_bytes, bar);
+    }
+  };
+  if (n_tiles > 0) issue(0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) issue(t + 1);   // its buffer was released by the barrier that ended tile t - 1
+    mbar_wait(&s_bar[t & 1], (unsigned)((t >> 1) & 1));
+    MT* raw = rawbase + (size_t)(t & 1) * rawSize;
+    const int pb = t * P, ch = pb >> 5, lane0 = pb & 31;
+    const int pmax = min(P, A.n_valid - pb);
+    const bool pvalid = p_t < pmax;
+    // -------- fix-up: subunit columns voted per (replicate, cell type); extra subunits of complexes folded in --------
+    for (int side = 0; side < 2; ++side) {
+      const int s0 = side ? nL : 0, nSide = side ? nR : nL;
+      MT* pl = raw + (size_t)side * 4 * planeSz;
+      for (int it = 0; it < n_ct_iter; ++it) {
+        const int ct_raw = ct0 + it * ctstep;
+        const bool ok = ct_raw < T;
+        const int ct = ok ? ct_raw : 0;
+        const int p = p_t, o = ct * PP + p;
+        MT m10 = pl[o], m11 = pl[planeSz + o], m20 = pl[2 * planeSz + o], m21 = pl[3 * planeSz + o];
+        {
+          const double d10 = (double)m10, d11 = (double)m11;
+          const double so = SO[ct * nS + s0];
+          const uint32_t v = __ballot_sync(0xffffffffu, ok && pvalid && fabs(d11 - d10) >= so);  // cond2 - cond1 (R/utils_cci.R:212-239)
+          uint32_t vb = 0;
+          if (BAND) vb = __ballot_sync(0xffffffffu, ok && pvalid && band_diff(d11, d10, so, rt));
+          if (gleader && ok) {
+            CNT[ct * nS + s0] += __popc(v & gmask);
+            if (BAND) BND[ct * nS + s0] += __popc(vb & gmask);
+          }
+        }
+        for (int k = 1; k < nSide; ++k) {
+          const int g = s_gs[s0 + k];  // block-uniform
+          if (g >= 0) {
+            const size_t i0 = (((size_t)ch * A.G + g) * K + ct) * 32 + lane0 + p, i1 = i0 + (size_t)T * 32;
+            const MT a10 = M1[i0], a11 = M1[i1], a20 = M2[i0], a21 = M2[i1];
+            m10 = a10 < m10 ? a10 : m10; m11 = a11 < m11 ? a11 : m11;   // means are never NaN: plain minimum
+            m20 = a20 < m20 ? a20 : m20; m21 = a21 < m21 ? a21 : m21;
+            const double d10 = (double)a10, d11 = (double)a11;
+            const double so = SO[ct * nS + s0 + k];
+            const uint32_t v = __ballot_sync(0xffffffffu, ok && pvalid && fabs(d11 - d10) >= so);
+            uint32_t vb = 0;
+            if (BAND) vb = __ballot_sync(0xffffffffu, ok && pvalid && band_diff(d11, d10, so, rt));
+            if (gleader && ok) {
+              CNT[ct * nS + s0 + k] += __popc(v & gmask);
+              if (BAND) BND[ct * nS + s0 + k] += __popc(vb & gmask);
+            }
+          }
+        }
+        if (ok && has_extra) { pl[o] = m10; pl[planeSz + o] = m11; pl[2 * planeSz + o] = m20; pl[3 * planeSz + o] = m21; }
+      }
+    }
+    if (has_extra) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes to the tile before a later bulk copy into it
+      __syncthreads();
+    }
+    // ---------------- rows: V replicates per 16-byte vector ----------------
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if (rid[q] < 0) continue;
+      const double aob0 = fabs(ob[q][0]);
+      const double o2a = ob[q][1] * ob[q][1], o2b = ob[q][2] * ob[q][2];
+      uint32_t c0 = 0, c1 = 0, c2 = 0, b0 = 0, b1 = 0, b2 = 0;
+      const MT* le = raw + e_[q] * PP;                           // emitter side planes 0..3
+      const MT* rr = raw + (size_t)4 * planeSz + r_[q] * PP;     // receiver side planes 4..7
+      for (int p0 = 0; p0 < pmax; p0 += V) {
+        MT Lm[4][V], Rm[4][V];   // [pass * 2 + cond][replicate], widened on use
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (F32) {
+            const float4 a = *reinterpret_cast<const float4*>(le + (size_t)k * planeSz + p0);
+            const float4 b = *reinterpret_cast<const float4*>(rr + (size_t)k * planeSz + p0);
+            Lm[k][0] = a.x; Lm[k][1] = a.y; Lm[k][V - 2] = a.z; Lm[k][V - 1] = a.w;
+            Rm[k][0] = b.x; Rm[k][1] = b.y; Rm[k][V - 2] = b.z; Rm[k][V - 1] = b.w;
+          } else {
+            const double2 a = *reinterpret_cast<const double2*>(le + (size_t)k * planeSz + p0);
+            const double2 b = *reinterpret_cast<const double2*>(rr + (size_t)k * planeSz + p0);
+            Lm[k][0] = a.x; Lm[k][V - 1] = a.y;
+            Rm[k][0] = b.x; Rm[k][V - 1] = b.y;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (p0 + v < pmax) {
+            if (A.score_type == 0) {
+              c0 += de_exceeds<BAND>((double)Lm[1][v] * (double)Rm[1][v], (double)Lm[0][v] * (double)Rm[0][v], aob0, kslack, rt, b0) ? 1u : 0u;
+              const double xa = (double)Lm[2][v] * (double)Rm[2][v], xb = (double)Lm[3][v] * (double)Rm[3][v];
+              c1 += (xa >= th[q][0]) ? 1u : 0u;
+              c2 += (xb >= th[q][1]) ? 1u : 0u;
+              if (BAND) {
+                b1 += band_product(xa, o2a, rt) ? 1u : 0u;
+                b2 += band_product(xb, o2b, rt) ? 1u : 0u;
+              }
+            } else {
+              const double sc1 = ((double)Lm[1][v] + (double)Rm[1][v]) / 2, sc0 = ((double)Lm[0][v] + (double)Rm[0][v]) / 2;
+              const double de = sc1 - sc0;
+              const double sa = ((double)Lm[2][v] + (double)Rm[2][v]) / 2, sb = ((double)Lm[3][v] + (double)Rm[3][v]) / 2;
+              c0 += (fabs(de) >= aob0) ? 1u : 0u;
+              c1 += (sa >= ob[q][1]) ? 1u : 0u;
+              c2 += (sb >= ob[q][2]) ? 1u : 0u;
+              if (BAND) {
+                b0 += band_diff(sc1, sc0, aob0, rt) ? 1u : 0u;
+                b1 += band_value(sa, ob[q][1], rt) ? 1u : 0u;
+                b2 += band_value(sb, ob[q][2], rt) ? 1u : 0u;
+              }
+            }
+          }
+        }
+      }
+      cnt[q][0] += c0; cnt[q][1] += c1; cnt[q][2] += c2;
+      if (BAND) { bnd[q][0] += b0; bnd[q][BAND ? 1 : 0] += b1; bnd[q][BAND ? 2 : 0] += b2; }
+    }
+    __syncthreads();  // everyone is done with RAW buffer t & 1 before the next bulk copies overwrite it
+  }
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rid[q] < 0) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A.counts[(size_t)c * A.R + rid[q]] += cnt[q][c];
+      if (BAND) A.band[(size_t)c * A.R + rid[q]] += bnd[q][BAND ? c : 0];
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < nS) {
+        const int fi = ((s < nL) ? e_[q] : r_[q]) * nS + s;
+        A.counts[(size_t)(3 + s) * A.R + rid[q]] += CNT[fi];
+        if (BAND) A.band[(size_t)(3 + s) * A.R + rid[q]] += BND[fi];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Observed-pass helper (aggregate_cells on the original labels): one thread per gene, sequential over the column.
 // out is column-major [K][G]: out[g*K + k]. mode 0: sum of x ; mode 1: sum of 1*(x > 0).
 // ------------------------------------------------------------------------------------------------------------------
@@ -2012,6 +2270,37 @@ __global__ void k_observed_rows(ObservedArgs A) {
 __global__ void k_widen_counts(size_t n, const uint32_t* __restrict__ in, long long* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (long long)in[i];
+}
+
+// Factorised subunit columns (k_score_diff FACT): the table obs_sub[L][T][nS] of the observed subunit differences shared
+// by all rows with the same (LRI, emitter) resp. (LRI, receiver). Built and verified on the device: k_fact_fill lets every
+// row store its values (the table starts as all-ones bit patterns = NaN; concurrent writers race, any winner will do),
+// k_fact_check then compares every row with the table bit for bit: if the rows of one pair disagree, at least one of them
+// differs from the winner and sets the flag (the host then takes the per-row path).
+__global__ void k_fact_fill(int R, int T, int nL, int nS, const int* __restrict__ row_lri, const int* __restrict__ row_emit,
+                            const int* __restrict__ row_recv, const double* __restrict__ obs, double* __restrict__ obs_sub) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int l = row_lri[r], e = row_emit[r], rc = row_recv[r];
+  for (int s = 0; s < nS; ++s)
+    obs_sub[((size_t)l * T + (s < nL ? e : rc)) * nS + s] = obs[(size_t)(3 + s) * R + r];
+}
+__global__ void k_fact_check(int R, int T, int nL, int nS, const int* __restrict__ row_lri, const int* __restrict__ row_emit,
+                             const int* __restrict__ row_recv, const double* __restrict__ obs,
+                             const double* __restrict__ obs_sub, int* __restrict__ mismatch) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int l = row_lri[r], e = row_emit[r], rc = row_recv[r];
+  for (int s = 0; s < nS; ++s) {
+    const double a = obs_sub[((size_t)l * T + (s < nL ? e : rc)) * nS + s], b = obs[(size_t)(3 + s) * R + r];
+    if (__double_as_longlong(a) != __double_as_longlong(b) && !(isnan(a) && isnan(b))) *mismatch = 1;
+  }
+}
+
+// counts[i] = 0xFFFFFFFF where the observed value is NaN (NA): the host maps it to SCDC_COUNT_NA (counts are <= 2e9)
+__global__ void k_mark_na(size_t n, const double* __restrict__ obs, uint32_t* __restrict__ counts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && isnan(obs[i])) counts[i] = 0xFFFFFFFFu;
 }
 
 // multi-GPU merge without NCCL: acc += add (a peer's counters copied over NVLink)

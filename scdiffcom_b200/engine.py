@@ -194,6 +194,17 @@ def merge_pvalues(n_full, tested_rows, counts_raw, iterations, sub_gene=None, lr
     return out
 
 
+def bh_adjust(p, group=None):
+    """`scdc_bh_adjust`: stats::p.adjust(p, method = "BH") (NaN = NA kept), optionally inside every `group`
+    (the reference's BH_P_VALUE* columns, R/utils_filtering.R:216-235)."""
+    lib = _lib.load()
+    p = _arr(p, np.float64)
+    g = None if group is None else _arr(group, np.int32)
+    out = np.empty_like(p)
+    check(lib.scdc_bh_adjust(p.size, _ptr(p), _ptr(g), _ptr(out)))
+    return out
+
+
 class Engine:
     """Handle API: the problem stays resident in HBM on one device across runs (`scdc_create` / `scdc_run`)."""
 

@@ -102,3 +102,37 @@ def test_argument_errors():
         engine.cci_template(3, 1, np.array([0, 0, 1]), np.zeros(5, np.int32))
     with pytest.raises(_lib.ScdcError, match="out of range"):
         engine.merge_pvalues(10, np.array([11]), np.zeros((1, 1), np.uint64), 10)
+
+
+def _p_adjust_bh(p):
+    """stats::p.adjust(p, "BH") restated in NumPy: NA left out, pmin(1, cummin(n / i * p[o]))[ro] over decreasing p."""
+    p = np.asarray(p, dtype=np.float64)
+    out = np.full_like(p, np.nan)
+    ok = ~np.isnan(p)
+    q = p[ok]
+    n = len(q)
+    if n:
+        o = np.argsort(-q, kind="stable")
+        adj = np.minimum(1.0, np.minimum.accumulate(n / np.arange(n, 0, -1) * q[o]))
+        r = np.empty(n)
+        r[o] = adj
+        out[ok] = r
+    return out
+
+
+def test_bh_adjustment_matches_p_adjust():
+    """f4: the BH_P_VALUE* columns of process_cci_raw (R/utils_filtering.R:216-235)."""
+    rng = np.random.default_rng(11)
+    p = np.round(rng.random(50_000), 3)                # many ties, like counts / iterations
+    p[rng.random(p.size) < 0.1] = np.nan               # NA subunits
+    p[:5] = [0.0, 1.0, 1.0, 0.0, np.nan]
+    got = engine.bh_adjust(p)
+    assert np.array_equal(got, _p_adjust_bh(p), equal_nan=True)
+    from scipy.stats import false_discovery_control    # an independent implementation (no NA support)
+    ok = ~np.isnan(p)
+    np.testing.assert_allclose(got[ok], false_discovery_control(p[ok], method="bh"), rtol=1e-14)
+    g = rng.integers(0, 7, size=p.size).astype(np.int32)
+    got_g = engine.bh_adjust(p, g)
+    for k in range(7):
+        assert np.array_equal(got_g[g == k], _p_adjust_bh(p[g == k]), equal_nan=True)
+    assert engine.bh_adjust(np.array([])).size == 0

@@ -49,7 +49,7 @@ def test_full_size_shuffled_labels_equal_the_oracle(workloads, name):
         # production batch (what bench.py times): one call over `iters` replicates == [0, 64) + [64, iters)
         whole = eng.run(iters, seed=seed)
         rest = eng.run(iters - N_ORACLE, seed=seed, perm_offset=N_ORACLE)
-        assert whole["stats"]["batch_size"] >= min(iters, 2048)
+        assert whole["stats"]["batch_size"] >= min(iters, 1024)
         assert _eq(np.nan_to_num(whole["counts"]), np.nan_to_num(want) + np.nan_to_num(rest["counts"])), "additivity"
     one = perm_counts(prob, N_ORACLE, seed=seed)                                 # one-shot C-ABI call (what .Call binds)
     assert _eq(one["counts"], want), "one-shot call"
@@ -70,7 +70,7 @@ def test_config2_production_batch_against_the_oracle_directly(workloads):
     _, pct = helpers.reference_like_labels(prob, n, seed=7)
     want, _ = oracle_c.perm_counts(prob, pct, None)
     got = perm_counts(prob, n, perm_ct=pct)
-    assert got["stats"]["batch_size"] >= 2048
+    assert got["stats"]["batch_size"] >= 1024
     assert _eq(got["counts"], want)
 
 
