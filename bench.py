@@ -288,15 +288,18 @@ class Runner:
             e2e_s, e2e_stats, e2e_checksum, e2e_steps = float("inf"), {"ms_upload": 0, "ms_device": 0, "ms_merge": 0, "n_gpus": 0}, None, 0
         elif rank == 0:
             for _ in range(e2e_warmup):   # the first cudaMalloc / cudaFree cycles of new sizes are slow
-                perm_counts(prob, world * iters, seed=seed, n_gpus=world, batch_size=args.batch, **kw)
+                perm_counts(prob, world * iters, seed=seed, n_gpus=world, batch_size=args.batch, as_float=False, **kw)
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
                 t_call = time.perf_counter()
-                r = perm_counts(prob, world * iters, seed=seed, n_gpus=world, batch_size=args.batch, **kw)
+                # as_float=False: the raw uint64 counters the C-ABI call returns (the .Call wrapper's view); the NumPy
+                # float64 / NaN copies the Python mirror makes for its own tables are not part of the call
+                r = perm_counts(prob, world * iters, seed=seed, n_gpus=world, batch_size=args.batch, as_float=False, **kw)
                 e2e_call_ms.append(round((time.perf_counter() - t_call) * 1e3, 2))
             e2e_s = time.perf_counter() - t0
             e2e_stats = r["stats"]
-            e2e_checksum = int(np.nansum(r["counts"]))
+            raw = r["counts_raw"]
+            e2e_checksum = int(raw[raw != np.uint64(2**64 - 1)].sum())
         if self.cpu_group is not None:
             dist.barrier(group=self.cpu_group)
         if rank != 0:
@@ -310,12 +313,13 @@ class Runner:
         wavefronts = sum(s["reduce_wavefronts"] for s in stats_acc)
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_peak = 148 * sm_clock * 1e6          # one shared-memory wavefront per clock per SM
-        pipe = {"bound": "shared-memory data pipe (1 wavefront / clk / SM)", "unit": "wavefronts/s",
+        pipe = {"bound": "SM load-store data pipe (1 wavefront / clk / SM: shared-memory accesses and global-load write-backs)", "unit": "wavefronts/s",
                 "achieved": wavefronts / (ms_reduce / 1e3) if ms_reduce > 0 else 0.0, "peak": pipe_peak,
                 "frac": (wavefronts / (ms_reduce / 1e3) / pipe_peak) if ms_reduce > 0 else 0.0,
                 "wavefronts_per_launch": wavefronts / max(1, launches), "sm_mhz": sm_clock,
-                "note": "design wavefronts of the kernels (entry broadcast + accumulator read-modify-write), label loads "
-                        "excluded; ncu l1tex__throughput of the same launches is in profiles/ (NOTES_r2.md)"}
+                "note": "design wavefronts of k_scatter (entry broadcast + label load + accumulator read-modify-write) over the "
+                        "CUDA-event time of the whole reduction (k_pass1_cond runs next to it in differential mode); ncu "
+                        "l1tex__throughput of k_scatter alone is in profiles/NOTES_r2.md (76.6 % at K = 120, 96.9 % at K = 50)"}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):

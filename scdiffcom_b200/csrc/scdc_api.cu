@@ -5,11 +5,14 @@
 //   SCDC_TIMING=1            host phase times on stderr
 //   SCDC_URN_LABELS=1        sequential urn label generator instead of the random-key kernels (also read by the oracle)
 //   SCDC_BMAX, SCDC_SUPER_BATCH   cap of the reduction batch / of the label super-batch (replicates)
-//   SCDC_J, SCDC_W, SCDC_U, SCDC_PAIR   k_scatter: replicates per lane, warps per block, label prefetch depth, pair mode
-//   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1   k_pass1_cond: prefetch depth, warps per block, run next to k_scatter (default 1)
-//   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE   K3 variants
+//   SCDC_J, SCDC_J32, SCDC_W, SCDC_U, SCDC_PAIR   k_scatter: replicates per lane (fp64 / fp32), warps per block, (value, label)
+//                            slots per lane, entries per dependent step (0 / 1 / 2 -> 1 / 2 / 4)
+//   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1, SCDC_P1_PERSISTENT, SCDC_P1_BLOCKS   k_pass1_cond: records per pipeline stage, warps per
+//                            block, run next to k_scatter (default 1) as a persistent grid (default 1) of n blocks per SM
+//   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE, SCDC_SCORE_BULK   K3 variants
 //   SCDC_NO_EARLY_REDUCE, SCDC_CHUNK_NNZ, SCDC_NO_PRELAUNCH   one-shot call: no reduction behind the upload, chunk size,
 //                            no label pre-launch
+//   SCDC_NO_NCCL=1, SCDC_BCAST_NCCL=1   multi-GPU call: peer copies + adds instead of ncclAllReduce / ncclBroadcast for the problem
 //   SCDC_NO_POOL, SCDC_NO_STAGER   plain cudaMalloc / plain pageable copies
 #include "../../include/scdc.h"
 #include "scdc_kernels.cuh"
@@ -308,6 +311,14 @@ struct scdc_handle {
 namespace {
 
 constexpr int kScoreThreads = 256, kScoreRPT = 2;
+// multi-GPU call: invoked by create_impl on the first device as soon as the matrix, the cell labels and the list of active
+// genes are on the device and batch 0's scatter is running there (phase A of the cloning: the other devices get the matrix
+// over NVLink and start their own labels / first scatter / pass-1 sort while the first device's host thread is still busy
+// with the rows)
+struct CreateHook {
+  virtual int matrix_ready(scdc_handle* root) = 0;
+  virtual ~CreateHook() {}
+};
 int prelaunch_labels(scdc_handle* h, const scdc_options* o);
 int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, const scdc_options* o,
                                        std::atomic<int>& genes_valid, std::atomic<bool>& matrix_done, const int& matrix_rc);
@@ -659,9 +670,54 @@ static int open_device_context(scdc_handle* h, int device) {
   return SCDC_OK;
 }
 
+// Cell labels and everything derived from them alone (8-bit codes, group sizes, K1 visit order, largest strata): what
+// the label generators need. Synchronises `s` (the staging vectors are local).
+static int install_labels(scdc_handle* h, const scdc_problem* p, cudaStream_t s) {
+  const int N = h->N, T = h->T, C = h->C, K = h->K;
+  try {
+    std::vector<uint8_t> ct8(N), cond8(N, 0);
+    std::vector<uint32_t> ng((size_t)K, 0);
+    for (int i = 0; i < N; ++i) {
+      ct8[i] = (uint8_t)p->ct_code[i];
+      if (C == 2) cond8[i] = (uint8_t)p->cond_code[i];
+      ++ng[(size_t)cond8[i] * T + ct8[i]];
+    }
+    std::vector<double> ngd(K);
+    for (int k = 0; k < K; ++k) ngd[k] = (double)ng[k];
+    h->max_nt = h->max_nc = 0;
+    for (int t = 0; t < T; ++t) h->max_nt = std::max(h->max_nt, (int)(ng[t] + (C == 2 ? ng[(size_t)T + t] : 0u)));
+    for (int c = 0; c < C; ++c) {
+      uint32_t n_c = 0;
+      for (int t = 0; t < T; ++t) n_c += ng[(size_t)c * T + t];
+      h->max_nc = std::max(h->max_nc, (int)n_c);
+    }
+    // K1 visit order: differential mode walks the cells grouped by cell type (stable), detection mode in cell order
+    std::vector<int> visit, ct_seg;
+    if (C == 2) {
+      visit.resize(N);
+      ct_seg.assign((size_t)T + 1, 0);
+      for (int i = 0; i < N; ++i) ++ct_seg[(size_t)ct8[i] + 1];
+      for (int t = 0; t < T; ++t) ct_seg[(size_t)t + 1] += ct_seg[t];
+      std::vector<int> cur(ct_seg.begin(), ct_seg.end() - 1);
+      for (int i = 0; i < N; ++i) visit[cur[ct8[i]]++] = i;
+      CU(h->visit.upload(visit.data(), visit.size(), s));
+      CU(h->ct_seg.upload(ct_seg.data(), ct_seg.size(), s));
+    }
+    CU(h->ct.upload(ct8.data(), N, s));
+    CU(h->cond.upload(cond8.data(), N, s));
+    CU(h->ngroup.upload(ngd.data(), K, s));
+    CU(h->expect.upload(ng.data(), K, s));
+    CU(cudaStreamSynchronize(s));
+  } catch (const std::bad_alloc&) {
+    return fail(SCDC_ENOMEM, "host allocation failed while staging the labels");
+  }
+  return SCDC_OK;
+}
+
 // o_hint != NULL (one-shot path): the options of the run that follows. The cheap part of the validation has been done by
 // the caller; the O(nnz) matrix check runs on a helper thread and K1 is launched ahead, both overlapping the H2D copies.
-static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, const scdc_options* o_hint) {
+static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out, const scdc_options* o_hint,
+                       CreateHook* hook = nullptr) {
   if (!out) return fail(SCDC_EINVAL, "out is NULL");
   *out = nullptr;
   PhaseTimer pt;
@@ -713,38 +769,9 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
   const int N = h->N, G = h->G, T = h->T, C = h->C, K = h->K;
   cudaStream_t s = h->stream;
   try {
-    std::vector<uint8_t> ct8(N), cond8(N, 0);
-    std::vector<uint32_t> ng((size_t)K, 0);
-    for (int i = 0; i < N; ++i) {
-      ct8[i] = (uint8_t)p->ct_code[i];
-      if (C == 2) cond8[i] = (uint8_t)p->cond_code[i];
-      ++ng[(size_t)cond8[i] * T + ct8[i]];
-    }
-    std::vector<double> ngd(K);
-    for (int k = 0; k < K; ++k) ngd[k] = (double)ng[k];
-    for (int t = 0; t < T; ++t) h->max_nt = std::max(h->max_nt, (int)(ng[t] + (C == 2 ? ng[(size_t)T + t] : 0u)));
-    for (int c = 0; c < C; ++c) {
-      uint32_t n_c = 0;
-      for (int t = 0; t < T; ++t) n_c += ng[(size_t)c * T + t];
-      h->max_nc = std::max(h->max_nc, (int)n_c);
-    }
-    // K1 visit order: differential mode walks the cells grouped by cell type (stable), detection mode in cell order
-    std::vector<int> visit, ct_seg;
-    if (C == 2) {
-      visit.resize(N);
-      ct_seg.assign((size_t)T + 1, 0);
-      for (int i = 0; i < N; ++i) ++ct_seg[(size_t)ct8[i] + 1];
-      for (int t = 0; t < T; ++t) ct_seg[(size_t)t + 1] += ct_seg[t];
-      std::vector<int> cur(ct_seg.begin(), ct_seg.end() - 1);
-      for (int i = 0; i < N; ++i) visit[cur[ct8[i]]++] = i;
-      CU(h->visit.upload(visit.data(), visit.size(), s));
-      CU(h->ct_seg.upload(ct_seg.data(), ct_seg.size(), s));
-    }
+    rc = install_labels(h.get(), p, s);
+    if (rc) return rc;
     CU(h->colptr.upload(p->colptr, (size_t)G + 1, s));
-    CU(h->ct.upload(ct8.data(), N, s));
-    CU(h->cond.upload(cond8.data(), N, s));
-    CU(h->ngroup.upload(ngd.data(), K, s));
-    CU(h->expect.upload(ng.data(), K, s));
     pt.lap("create: context + small prep");
     if (o_hint) {  // K1 needs only the labels: draw the first super-batch while the matrix is copied
       rc = prelaunch_labels(h.get(), o_hint);
@@ -808,6 +835,11 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       // the rows' uploads and small kernels go to the HIGH-priority label stream (idle by now): on a low-priority stream
       // their blocks starved behind the scatter's 24 k blocks and create waited ~350 ms for them (SCDC_TIMING, config 5)
       if (h->pre.k2_done) s_up = h->stream_labels;
+      if (hook && h->pre.k2_done) {
+        rc = hook->matrix_ready(h.get());
+        if (rc) return rc;
+        CU(cudaSetDevice(device));
+      }
     }
     if (C == 2) {
       // pass-1 copy of the matrix (inside each gene column, entries stably sorted by cell type), built on the device from
@@ -988,10 +1020,10 @@ template <typename VT> const VT* matrix_values(const scdc_handle* h);
 template <> const double* matrix_values<double>(const scdc_handle* h) { return h->values.p; }
 template <> const float* matrix_values<float>(const scdc_handle* h) { return h->values_f.p; }
 
-template <typename VT, int J, int U, bool PAIR>
+template <typename VT, int J, int U, int GRP>
 cudaError_t launch_scatter_u(const scdc_handle* h, const ScatterPlan& pl, int Bpad, const uint8_t* lab2, int lab_stride,
                              void* M2, cudaStream_t s, const int* genes, int n_genes) {
-  auto kern = scdc::k_scatter<VT, J, U, PAIR>;
+  auto kern = scdc::k_scatter<VT, J, U, GRP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   const int nCJ = Bpad / (32 * J);
@@ -1012,17 +1044,18 @@ cudaError_t launch_scatter_j(const scdc_handle* h, const ScatterPlan& pl, int Bp
     // (K = 120): fp64, 7 warps / SM: U = 32 343 ms vs U = 16 430 ms per 2560 replicates; fp32, 14 warps / SM: U = 16
     // 486 ms per 6400 vs U = 32 695 ms (U = 32 halves the resident warps there).
     const int U = env_int("SCDC_U", warps_per_sm <= 8 ? 32 : (warps_per_sm <= 24 ? 16 : 8));
+    // entries per dependent step (SCDC_PAIR = 0 / 1 / 2 -> 1 / 2 / 4)
     const int pair = env_int("SCDC_PAIR", (warps_per_sm <= 16) ? 1 : 0);
-#define SCDC_GO(UU, PP) return launch_scatter_u<VT, 1, UU, PP>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes)
-    if (U >= 32) { if (pair) SCDC_GO(32, true); SCDC_GO(32, false); }
-    if (U >= 16) { if (pair) SCDC_GO(16, true); SCDC_GO(16, false); }
-    if (pair) SCDC_GO(8, true);
-    SCDC_GO(8, false);
+#define SCDC_GO(UU, GG) return launch_scatter_u<VT, 1, UU, GG>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes)
+    if (U >= 32) { if (pair >= 2) SCDC_GO(32, 4); if (pair) SCDC_GO(32, 2); SCDC_GO(32, 1); }
+    if (U >= 16) { if (pair >= 2) SCDC_GO(16, 4); if (pair) SCDC_GO(16, 2); SCDC_GO(16, 1); }
+    if (pair) SCDC_GO(8, 2);
+    SCDC_GO(8, 1);
 #undef SCDC_GO
   } else {
     const int U = env_int("SCDC_U", 16);
-    if (U >= 16) return launch_scatter_u<VT, J, 16, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
-    return launch_scatter_u<VT, J, 8, false>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    if (U >= 16) return launch_scatter_u<VT, J, 16, 1>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
+    return launch_scatter_u<VT, J, 8, 1>(h, pl, Bpad, lab2, lab_stride, M2, s, genes, n_genes);
   }
 }
 
@@ -1075,17 +1108,15 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
     // equal batches: the reduction always runs whole batches, so n batches of the smallest multiple of q that covers
     // iterations / n waste at most q - 1 replicates per batch (10 000 -> 1 x 10 112 instead of 3 x 4096); among the batch
     // counts that fit the memory budget (and up to twice the minimum) take the one that pads least
-    // ... where "pads" counts what the scatter really runs: whole blocks of W warps x 32 J replicates (config 5, 12 500
-    // replicates: 5 x 2560 would run 5 x 84 chunks for 80 useful ones each, 7 x 1792 runs 7 x 56 full ones)
+    // (Counting whole scatter blocks of W warps x 32 J replicates as well — config 5: 7 x 1792 replicates = 7 x 56 full
+    // chunks instead of 5 x 2560 = 5 x 80 chunks in 84 slots — was measured SLOWER, 1969 vs 1900 ms of reduction per 12 500
+    // replicates: every batch pays the tails of three kernels.)
     const long long n_min = (o->iterations + B - 1) / B;
     long long best_B = 0, best_total = 0;
-    for (long long n = n_min; n <= 3 * n_min + 1; ++n) {
+    for (long long n = n_min; n <= 2 * n_min; ++n) {
       const long long Bn = (((o->iterations + n - 1) / n + q - 1) / q) * q;
       if (Bn > B) continue;
-      const ScatterPlan pn = plan_scatter(h, (int)Bn, o->precision == SCDC_FP32_FAST);
-      const long long slice = 32LL * pn.J * pn.W;
-      const long long total = n * (((Bn + slice - 1) / slice) * slice);
-      if (!best_B || total < best_total) { best_B = Bn; best_total = total; }
+      if (!best_B || n * Bn < best_total) { best_B = Bn; best_total = n * Bn; }
     }
     if (best_B) B = best_B;
   } else {
@@ -1521,12 +1552,11 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
                     (double)B * N * (C == 2 ? 1.125 : 1.0) + (double)C * B * K * h->n_active * sv;
-    // shared-memory wavefronts by design: per (entry x 32J replicates) the scatter issues a 2-wavefront entry broadcast,
-    // J x (LDS.64 + STS.64) = 4J and 4/32 for the staging store; pass 1 only the broadcast and the staging store.
-    // fp32: 1-wavefront broadcast (LDS.64), J x (LDS.32 + STS.32) = 2J, 2/32 for the staging store.
+    // load-store data-pipe wavefronts of the scatter by design, per (entry x 32 J replicates): entry broadcast (fp64 LDS.128 =
+    // 2, fp32 LDS.64 = 1), the write-back of the warp's label load (32 J bytes = 1), J x (LDS + STS) (fp64 4 J, fp32 2 J) and
+    // the staging store (4/32 resp. 2/32). Pass 1 (k_pass1_cond) uses no shared memory and is not counted.
     const double wf_b = f32 ? 1.0 : 2.0, wf_rmw = f32 ? 2.0 : 4.0, wf_st = f32 ? 0.0625 : 0.125;
-    reduce_wavefronts += (double)h->nnz_active * (B / (32.0 * pl.J)) * (wf_b + wf_rmw * pl.J + wf_st) +
-                         0.0;  // pass 1 (k_pass1_cond) uses no shared memory
+    reduce_wavefronts += (double)h->nnz_active * (B / (32.0 * pl.J)) * (wf_b + 1.0 + wf_rmw * pl.J + wf_st);
     CU(mark(evs, s));
     if (overlap_score) {
       CU(cudaEventRecord(m_ready[mb], s));
@@ -1560,9 +1590,12 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
           kern<<<h->n_tasks, h->score_threads, smem_k, sS>>>(D);
           return cudaGetLastError();
         };
-        if (fact && env_int("SCDC_SCORE_BULK", 1)) {
-          // tiles in the means' natural layout, filled by cp.async.bulk + mbarrier (k_score_diff_bulk): rows padded to
-          // P + 2 (fp64) / P + 4 (fp32) elements, two buffers of 8 planes x T rows
+        if (fact && env_int("SCDC_SCORE_BULK", 0)) {
+          // OPT-IN (SCDC_SCORE_BULK=1): tiles in the means' natural layout, filled by cp.async.bulk + mbarrier
+          // (k_score_diff_bulk): rows padded to P + 2 (fp64) / P + 4 (fp32) elements, two buffers of 8 planes x T rows.
+          // Correct (the whole GPU suite passes with it) but measured SLOWER than the cp.async kernel: config 5 score
+          // 436 vs 307 ms per 12.8 k replicates, config 3 60.7 vs 50.2 ms per 10 k (profiles/NOTES_r2.md, r2j): a tile is
+          // 8 T pieces of only P x 8 = 64 bytes, and 480 tiny bulk copies per tile cost more than they save.
           const size_t es = f32 ? 4 : 8;
           const int pad = f32 ? 4 : 2;
           int Pb = 32;
@@ -1773,53 +1806,69 @@ struct Mirror {
   size_t bytes;
 };
 
-// Copies every Mirror from device hs[0] to the devices of hs[1..]: ncclBroadcast over NVLink when NCCL is available, else
-// cudaMemcpyPeerAsync from the root. Enqueued on each twin's stream; on the root the NCCL kernels go to `root_stream`, a
-// high-priority stream of their own, because the root's compute stream is already busy with its first batch.
+// Copies every Mirror from device hs[0] to the devices of hs[1..] on the given per-device streams: ncclBroadcast over
+// NVLink when NCCL is available, else cudaMemcpyPeerAsync from the root.
 int broadcast_mirrors(const std::vector<scdc_handle*>& hs, const std::vector<Mirror>& ms, bool use_nccl,
-                      cudaStream_t root_stream) {
+                      const std::vector<cudaStream_t>& streams) {
   const int W = (int)hs.size();
   for (const Mirror& m : ms) {
     if (!m.bytes) continue;
     if (use_nccl) {
       int nrc = g_nccl.GroupStart();
       for (int r = 0; r < W && nrc == 0; ++r)
-        nrc = g_nccl.Broadcast(m.src, m.dst[r], m.bytes, kNcclUint8, 0, g_comms[r], r ? hs[r]->stream : root_stream);
+        nrc = g_nccl.Broadcast(m.src, m.dst[r], m.bytes, kNcclUint8, 0, g_comms[r], streams[r]);
       const int erc = g_nccl.GroupEnd();
       if (nrc != 0 || erc != 0)
         return fail(SCDC_ENCCL, "ncclBroadcast failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc ? nrc : erc) : "?");
     } else {
       for (int r = 1; r < W; ++r)
-        CU(cudaMemcpyPeerAsync(m.dst[r], hs[r]->device, m.src, hs[0]->device, m.bytes, hs[r]->stream));
+        CU(cudaMemcpyPeerAsync(m.dst[r], hs[r]->device, m.src, hs[0]->device, m.bytes, streams[r]));
     }
     g_p2p_bytes += (double)m.bytes * (W - 1);
   }
   return SCDC_OK;
 }
 
-// The twins of a fully created handle on other devices: same problem, same rows, nothing read from the caller's host
-// arrays again. Allocates the twins' device buffers (each in its own stream's order) and fills `ms` with what to copy.
-int clone_handles(std::vector<scdc_handle*>& hs, const std::vector<int>& devs, std::vector<Mirror>& ms) {
-  scdc_handle* h0 = hs[0];
-  const int W = (int)hs.size();
-  for (int r = 1; r < W; ++r) {
-    std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
-    if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
-    int rc = open_device_context(h.get(), devs[r]);
-    if (rc) return rc;
-    h->N = h0->N; h->G = h0->G; h->T = h0->T; h->C = h0->C; h->L = h0->L; h->R = h0->R; h->nL = h0->nL; h->nR = h0->nR;
-    h->K = h0->K; h->ncols = h0->ncols; h->nS = h0->nS; h->nnz = h0->nnz;
-    h->fact_ok = h0->fact_ok; h->n_tasks = h0->n_tasks; h->score_threads = h0->score_threads;
-    h->sub_gene_h = h0->sub_gene_h; h->gene_nnz_h = h0->gene_nnz_h;
-    h->max_nt = h0->max_nt; h->max_nc = h0->max_nc; h->n_active = h0->n_active; h->nnz_active = h0->nnz_active;
-    h->one_shot = true;
-    hs[r] = h.release();
+// ---- the twins of the first device's handle on the other devices of a multi-GPU call -----------------------------------
+// Nothing big is read from the caller's host arrays twice: the problem travels device to device over NVLink —
+// ncclBroadcast (cudaMemcpyPeerAsync when NCCL is unavailable: SCDC_NO_NCCL=1) on a dedicated high-priority stream per
+// device, because the devices' compute streams are busy with their first batch by then and an NCCL kernel that waits for
+// its peers at the rendezvous spins on SMs. Three phases, so that the twins lag the first device as little as possible:
+//   phase 0 (before create): contexts, the cell labels (N bytes, from the host) and each twin's own label draw;
+//   phase A (from create_impl's hook, as soon as the matrix is on the first device and its first scatter is running, while
+//            its host thread still has the rows to do): CSC matrix, LRI table, active genes; every twin then starts the
+//            scatter of its first batch and builds its pass-1 copy of the matrix locally (k_sort_by_celltype);
+//   phase B (after create): tested rows, observed values, thresholds, K3 work list, factorisation table.
+struct MultiGpuCall : CreateHook {
+  std::vector<scdc_handle*> hs;
+  std::vector<int> devs;
+  std::vector<scdc_options> os;
+  const scdc_problem* prob = nullptr;
+  bool use_nccl = false, phase_a_done = false;
+  std::vector<cudaStream_t> bs;    // broadcast stream of every device (high priority; the compute streams are busy)
+
+  int open_broadcast_streams() {
+    bs.assign(devs.size(), nullptr);
+    for (size_t r = 0; r < devs.size(); ++r) {
+      CU(cudaSetDevice(devs[r]));
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&bs[r], cudaStreamNonBlocking, hi));
+    }
+    return SCDC_OK;
   }
-  size_t idx = 0;
-  auto mirror = [&](auto member) -> int {   // member: pointer to a DBuf member of scdc_handle
+  void close_broadcast_streams() {
+    for (size_t r = 0; r < bs.size(); ++r)
+      if (bs[r]) { cudaSetDevice(devs[r]); cudaStreamSynchronize(bs[r]); cudaStreamDestroy(bs[r]); bs[r] = nullptr; }
+  }
+
+  template <typename M>
+  int mirror(std::vector<Mirror>& ms, M member) {   // member: pointer to a DBuf member of scdc_handle
+    scdc_handle* h0 = hs[0];
+    const int W = (int)hs.size();
     auto& src = h0->*member;
-    if (ms.size() <= idx) ms.resize(idx + 1);
-    Mirror& m = ms[idx++];
+    ms.emplace_back();
+    Mirror& m = ms.back();
     m.src = src.p;
     m.bytes = src.p ? src.n * sizeof(*src.p) : 0;
     m.dst.assign(W, nullptr);
@@ -1832,26 +1881,167 @@ int clone_handles(std::vector<scdc_handle*>& hs, const std::vector<int>& devs, s
       m.dst[r] = d.p;
     }
     return SCDC_OK;
-  };
-#define SCDC_MIRROR(member)                      \
-  do {                                           \
-    int rc_ = mirror(&scdc_handle::member);      \
-    if (rc_) return rc_;                         \
-  } while (0)
-  SCDC_MIRROR(colptr); SCDC_MIRROR(rowidx); SCDC_MIRROR(values); SCDC_MIRROR(segptr); SCDC_MIRROR(rec_s);
-  SCDC_MIRROR(values_f); SCDC_MIRROR(rec_sf);
-  SCDC_MIRROR(gene_order); SCDC_MIRROR(sub_gene); SCDC_MIRROR(row_lri); SCDC_MIRROR(row_emit); SCDC_MIRROR(row_recv);
-  SCDC_MIRROR(ngroup); SCDC_MIRROR(obs); SCDC_MIRROR(ct); SCDC_MIRROR(cond); SCDC_MIRROR(expect); SCDC_MIRROR(visit);
-  SCDC_MIRROR(ct_seg); SCDC_MIRROR(task_lri); SCDC_MIRROR(task_beg); SCDC_MIRROR(task_end); SCDC_MIRROR(srow);
-  SCDC_MIRROR(thr); SCDC_MIRROR(obs_sub);
-#undef SCDC_MIRROR
-  for (int r = 1; r < W; ++r) {
-    CU(cudaSetDevice(hs[r]->device));
-    AllocScope scope(hs[r]->stream);
-    CU(hs[r]->flag.alloc(1));
   }
-  return SCDC_OK;
-}
+#define SCDC_MIRROR(member)                          \
+  do {                                               \
+    int rc_ = mirror(ms, &scdc_handle::member);      \
+    if (rc_) return rc_;                             \
+  } while (0)
+
+  // device `to` may read / write the stream-ordered allocations of device `of` (pool memory needs cudaMemPoolSetAccess;
+  // cudaDeviceEnablePeerAccess covers plain cudaMalloc memory, SCDC_NO_POOL=1)
+  static void allow_peer(int of, int to) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, of) == cudaSuccess) {
+      cudaMemAccessDesc d;
+      memset(&d, 0, sizeof d);
+      d.location.type = cudaMemLocationTypeDevice;
+      d.location.id = to;
+      d.flags = cudaMemAccessFlagsProtReadWrite;
+      cudaMemPoolSetAccess(pool, &d, 1);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(to);
+    cudaDeviceEnablePeerAccess(of, 0);
+    cudaSetDevice(cur);
+    cudaGetLastError();  // "already enabled" / unsupported: peer copies then fall back to staging, still correct
+  }
+
+  // Broadcast on the devices' broadcast streams, ordered after everything enqueued so far on every device's compute stream
+  // (the root's uploads, the twins' allocations); the twins' compute streams then wait for the arrival.
+  int broadcast_ordered(const std::vector<Mirror>& ms) {
+    const int W = (int)hs.size();
+    for (int r = 0; r < W; ++r) {
+      CU(cudaSetDevice(hs[r]->device));
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaError_t e = cudaEventRecord(ev, hs[r]->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(bs[r], ev, 0);
+      cudaEventDestroy(ev);
+      CU(e);
+    }
+    if (!use_nccl) {  // peer copies run on the twins' streams only: they must see the root's data
+      CU(cudaSetDevice(hs[0]->device));
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaError_t e = cudaEventRecord(ev, hs[0]->stream);
+      for (int r = 1; r < W && e == cudaSuccess; ++r) e = cudaStreamWaitEvent(bs[r], ev, 0);
+      cudaEventDestroy(ev);
+      CU(e);
+    }
+    int rc = broadcast_mirrors(hs, ms, use_nccl, bs);
+    if (rc) return rc;
+    for (int r = 1; r < W; ++r) {
+      CU(cudaSetDevice(hs[r]->device));
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaError_t e = cudaEventRecord(ev, bs[r]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(hs[r]->stream, ev, 0);
+      cudaEventDestroy(ev);
+      CU(e);
+    }
+    return SCDC_OK;
+  }
+
+  int phase_0(int root_device) {
+    const int W = (int)hs.size();
+    const scdc_problem* p = prob;
+    for (int r = 1; r < W; ++r) {
+      std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
+      if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
+      int rc = open_device_context(h.get(), devs[r]);
+      if (rc) return rc;
+      allow_peer(root_device, devs[r]);
+      allow_peer(devs[r], root_device);
+      if (getenv("SCDC_TIMING")) {
+        int can = -1;
+        cudaDeviceCanAccessPeer(&can, devs[r], root_device);
+        fprintf(stderr, "[scdc timing] device %d can access device %d directly: %d; broadcast / merge by %s\n", devs[r], root_device,
+                can, use_nccl ? "NCCL" : "peer copies");
+      }
+      h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
+      h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
+      h->ncols = (h->C == 2) ? 3 + h->nS : 1;
+      h->nnz = (size_t)p->colptr[h->G];
+      h->one_shot = true;
+      hs[r] = h.release();
+      scdc_handle* hr = hs[r];
+      AllocScope scope(hr->stream);
+      rc = install_labels(hr, p, hr->stream);
+      if (!rc && os[r].iterations > 0) rc = prelaunch_labels(hr, &os[r]);
+      if (rc) return rc;
+    }
+    return SCDC_OK;
+  }
+
+  int phase_a(bool early_launches) {
+    scdc_handle* h0 = hs[0];
+    const int W = (int)hs.size();
+    for (int r = 1; r < W; ++r) {
+      hs[r]->sub_gene_h = h0->sub_gene_h; hs[r]->gene_nnz_h = h0->gene_nnz_h;
+      hs[r]->n_active = h0->n_active; hs[r]->nnz_active = h0->nnz_active;
+    }
+    std::vector<Mirror> ms;
+    SCDC_MIRROR(colptr); SCDC_MIRROR(rowidx); SCDC_MIRROR(values); SCDC_MIRROR(sub_gene); SCDC_MIRROR(gene_order);
+    PhaseTimer pt;
+    int rc = broadcast_ordered(ms);
+    if (rc) return rc;
+    if (pt.on) {  // SCDC_TIMING=1: wait for the copies so that their duration shows (changes the overlap it reports on)
+      for (int r = 1; r < W; ++r) { cudaSetDevice(hs[r]->device); cudaStreamSynchronize(hs[r]->stream); }
+      pt.lap("twins: matrix over NVLink");
+    }
+    for (int r = 1; r < W; ++r) {
+      scdc_handle* h = hs[r];
+      CU(cudaSetDevice(h->device));
+      AllocScope scope(h->stream);
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } evdel{ev};
+      CU(cudaEventRecord(ev, h->stream));  // the matrix has arrived
+      if (early_launches && h->C == 2 && h->pre.valid && h->n_active > 0) {
+        rc = launch_early_scatter(h, &os[r]);
+        if (rc) return rc;
+      }
+      if (h->C == 2) {  // pass-1 copy of the matrix, built locally on the high-priority stream next to the first scatter
+        cudaStream_t s_sort = h->stream_labels;
+        AllocScope sort_scope(s_sort);
+        CU(cudaStreamWaitEvent(s_sort, ev, 0));
+        rc = build_pass1_copy(h, s_sort);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev, s_sort));
+        CU(cudaStreamWaitEvent(h->stream, ev, 0));
+      }
+    }
+    CU(cudaSetDevice(h0->device));
+    phase_a_done = true;
+    return SCDC_OK;
+  }
+
+  int matrix_ready(scdc_handle* root) override {
+    hs[0] = root;
+    return phase_a(true);
+  }
+
+  int phase_b() {
+    scdc_handle* h0 = hs[0];
+    const int W = (int)hs.size();
+    for (int r = 1; r < W; ++r) {
+      hs[r]->R = h0->R; hs[r]->fact_ok = h0->fact_ok; hs[r]->n_tasks = h0->n_tasks; hs[r]->score_threads = h0->score_threads;
+      hs[r]->n_active = h0->n_active; hs[r]->nnz_active = h0->nnz_active;
+    }
+    std::vector<Mirror> ms;
+    SCDC_MIRROR(row_lri); SCDC_MIRROR(row_emit); SCDC_MIRROR(row_recv); SCDC_MIRROR(obs); SCDC_MIRROR(task_lri);
+    SCDC_MIRROR(task_beg); SCDC_MIRROR(task_end); SCDC_MIRROR(srow); SCDC_MIRROR(thr); SCDC_MIRROR(obs_sub);
+    for (int r = 1; r < W; ++r) {
+      CU(cudaSetDevice(hs[r]->device));
+      AllocScope scope(hs[r]->stream);
+      CU(hs[r]->flag.alloc(1));
+    }
+    return broadcast_ordered(ms);
+  }
+#undef SCDC_MIRROR
+};
 
 }  // namespace
 
@@ -1959,11 +2149,15 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   // range on its own host thread, and the uint32 counters are merged with one ncclAllReduce (or peer copies + adds).
   const double h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes, p2p0 = g_p2p_bytes;
   const bool f32 = o->precision == SCDC_FP32_FAST;
-  std::vector<scdc_handle*> hs(W, nullptr);
+  MultiGpuCall mg;
+  mg.hs.assign(W, nullptr);
+  mg.os.assign(W, *o);
+  mg.prob = p;
+  std::vector<scdc_handle*>& hs = mg.hs;
+  std::vector<scdc_options>& os = mg.os;
   std::vector<int> rcs(W, 0);
   std::vector<std::string> errs(W);
   std::vector<scdc_stats> sts(W);
-  std::vector<scdc_options> os(W, *o);
   const int64_t per = (o->iterations + W - 1) / W;
   for (int r = 0; r < W; ++r) {
     memset(&sts[r], 0, sizeof(scdc_stats));
@@ -1974,35 +2168,34 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     if (o->perm_ct) os[r].perm_ct = o->perm_ct + (size_t)b * p->n_cells;
     if (o->perm_cond) os[r].perm_cond = o->perm_cond + (size_t)b * p->n_cells;
   }
-  cudaStream_t root_bs = nullptr;  // the root's side of the NCCL broadcast
   auto cleanup = [&]() {
-    if (root_bs && hs[0]) { cudaSetDevice(hs[0]->device); cudaStreamSynchronize(root_bs); cudaStreamDestroy(root_bs); root_bs = nullptr; }
+    mg.close_broadcast_streams();
     for (auto h : hs) scdc_release(h);
   };
-  rc = create_impl(p, ids[0], &hs[0], &os[0]);  // W <= iterations / 128: every shard has replicates
-  if (rc) return rc;
-  pt.lap("perm_counts: create on the first device");
   std::lock_guard<std::mutex> comm_lock(g_nccl_mu);
-  std::vector<int> devs(ids.begin(), ids.begin() + W);
-  const bool use_nccl = nccl_comms_for(devs);
+  mg.devs.assign(ids.begin(), ids.begin() + W);
+  const bool use_nccl = mg.use_nccl = nccl_comms_for(mg.devs);
+  rc = mg.open_broadcast_streams();
+  if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+  rc = mg.phase_0(ids[0]);
+  if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+  pt.lap("perm_counts: twins' contexts + labels");
   {
-    std::vector<Mirror> ms;
-    if (f32) {  // the fp32 copies travel with the rest
-      CU(cudaSetDevice(hs[0]->device));
-      AllocScope scope(hs[0]->stream);
-      rc = ensure_f32_values(hs[0], hs[0]->stream, false);
-      if (!rc && hs[0]->C == 2) rc = ensure_f32_values(hs[0], hs[0]->stream, true);
-      if (!rc && cudaStreamSynchronize(hs[0]->stream) != cudaSuccess) rc = fail(SCDC_ECUDA, "fp32 conversion failed");
+    scdc_handle* h0 = nullptr;
+    rc = create_impl(p, ids[0], &h0, &os[0], &mg);  // W <= iterations / 128: every shard has replicates
+    if (rc) {  // twins made by the hook (mg.hs[0] is a handle create_impl has released itself)
+      const std::string keep = g_err;
+      hs[0] = nullptr;
+      cleanup();
+      g_err = keep;
+      return rc;
     }
-    if (!rc) rc = clone_handles(hs, devs, ms);
-    if (!rc && use_nccl && cudaSetDevice(hs[0]->device) == cudaSuccess) {
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      if (cudaStreamCreateWithPriority(&root_bs, cudaStreamNonBlocking, hi) != cudaSuccess) rc = fail(SCDC_ECUDA, "stream creation failed");
-    }
-    if (!rc) rc = broadcast_mirrors(hs, ms, use_nccl, root_bs);
-    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+    hs[0] = h0;
   }
+  pt.lap("perm_counts: create on the first device");
+  if (!mg.phase_a_done) rc = mg.phase_a(false);
+  if (!rc) rc = mg.phase_b();
+  if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
   pt.lap("perm_counts: broadcast");
   std::atomic<bool> abort_flag{false};
   std::atomic<int> workers_left{W};

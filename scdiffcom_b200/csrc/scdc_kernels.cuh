@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
 // Shared-memory wavefronts per (entry x 32 J replicates): fp64 2 (LDS.128 entry broadcast) + 4 J (LDS.64 + STS.64);
 // fp32 1 (LDS.64 broadcast) + 2 J (LDS.32 + STS.32): half the traffic through the pipe that bounds the kernel.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename VT, int J, int U, bool PAIR>
+template <typename VT, int J, int U, int GRP>
 __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr, const int* __restrict__ rowidx,
                           const VT* __restrict__ values, const uint8_t* __restrict__ lab2, int lab_stride,
                           const double* __restrict__ ngroup, const int* __restrict__ gene_order, VT* __restrict__ M2) {
@@ -1171,26 +1171,31 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
       // the slots hold entries [gq * U, gq * U + U) of stage s; their successors sit U entries further: in this stage's
       // buffer, or (last group of the stage) at the head of the next stage's
       const pack_t* src = (gq + 1 < 32 / U) ? (cur_buf + (gq + 1) * U) : nxt_buf;
-      if (PAIR && J == 1) {
-        // Two entries per step: both accumulators are loaded before either add. If the two labels coincide the second
-        // add continues from the first result, so the value stored last is ((acc + v1) + v2): the sequential sum, with a
-        // dependency chain of one shared-memory round trip per PAIR (matters when few warps are resident).
+      if (GRP == 4 && J == 1) {
+        // Four entries per step (few resident warps: more independent shared-memory loads in flight per lane). All four
+        // accumulators are loaded first; an entry whose label repeats an earlier one of the group continues from that
+        // entry's result, and the stores go out in entry order, so the value stored last for a label is the sequential sum.
 #pragma unroll
-        for (int u = 0; u < U; u += 2) {
+        for (int u = 0; u < U; u += 4) {
           VT* const p1 = reinterpret_cast<VT*>(accb + lb[u] * ROW);
           VT* const p2 = reinterpret_cast<VT*>(accb + lb[u + 1] * ROW);
-          const VT a1 = *p1, a2 = *p2;
+          VT* const p3 = reinterpret_cast<VT*>(accb + lb[u + 2] * ROW);
+          VT* const p4 = reinterpret_cast<VT*>(accb + lb[u + 3] * ROW);
+          const VT a1 = *p1, a2 = *p2, a3 = *p3, a4 = *p4;
           const VT r1 = a1 + val[u];
-          const VT r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
-          *p1 = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
-          *p2 = r2;
-          const pack_t e1 = src[u], e2 = src[u + 1];
-          val[u] = Ent<VT>::value(e1);
-          lb[u] = load_labels<J>(labbase + (uint64_t)e1.x * ustride);
-          val[u + 1] = Ent<VT>::value(e2);
-          lb[u + 1] = load_labels<J>(labbase + (uint64_t)e2.x * ustride);
+          const VT r2 = ((lb[u + 1] == lb[u]) ? r1 : a2) + val[u + 1];
+          const VT r3 = ((lb[u + 2] == lb[u + 1]) ? r2 : ((lb[u + 2] == lb[u]) ? r1 : a3)) + val[u + 2];
+          const VT r4 = ((lb[u + 3] == lb[u + 2]) ? r3 : ((lb[u + 3] == lb[u + 1]) ? r2 : ((lb[u + 3] == lb[u]) ? r1 : a4))) + val[u + 3];
+          *p1 = r1; *p2 = r2; *p3 = r3; *p4 = r4;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const pack_t en = src[u + w];
+            val[u + w] = Ent<VT>::value(en);
+            lb[u + w] = load_labels<J>(labbase + (uint64_t)en.x * ustride);
+          }
         }
-      } else {
+      } else if (GRP == 2 && J == 1) {
+        // Two entries per step: both accumulators are loaded before either add.      } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (J == 1) {

@@ -114,7 +114,10 @@ def _options(iterations, seed, score_type, perm_offset, n_gpus, batch_size, perm
     return o
 
 
-def _finish(problem, counts_f, dist, stats, band_f=None):
+def _finish(problem, counts_f, dist, stats, band_f=None, as_float=True):
+    if not as_float:   # raw uint64 counters (SCDC_COUNT_NA = NA): what the .Call wrapper receives, no float copies
+        return {"counts": None, "counts_raw": counts_f, "band_counts": None, "band_raw": band_f, "distributions": dist,
+                "stats": stats.as_dict()}
     na = counts_f == np.uint64(_lib.SCDC_COUNT_NA)
     counts = counts_f.astype(np.float64)
     counts[na] = np.nan
@@ -140,10 +143,11 @@ def version() -> str:
 
 def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="geometric_mean", n_gpus=1, perm_offset=0,
                 batch_size=0, perm_cond=None, perm_ct=None, return_distributions=False, device_base=0, interrupt=None,
-                precision="fp64", rel_tol=0.0):
+                precision="fp64", rel_tol=0.0, as_float=True):
     """One-shot `scdc_perm_counts` with HOST buffers (what the `.Call` wrapper does). Returns dict(counts [R_sub, ncols]
     float64 with NaN = NA, band_counts (precision="fp32_fast": comparisons inside the tolerance band) or None,
-    distributions or None, stats)."""
+    distributions or None, stats). as_float=False skips the float64 copies and returns only `counts_raw` (uint64 with
+    SCDC_COUNT_NA), i.e. exactly what the C-ABI call hands to the `.Call` wrapper."""
     lib = _lib.load()
     keep = []
     p = problem.c_struct()
@@ -162,7 +166,7 @@ def perm_counts(problem: PermutationProblem, iterations, seed=42, score_type="ge
         dist = np.zeros((int(iterations), ncd, problem.n_rows), dtype=np.float64)
         res.distributions = _ptr(dist)
     check(lib.scdc_perm_counts(C.byref(p), C.byref(o), C.byref(res)))
-    return _finish(problem, counts, dist, res.stats, band)
+    return _finish(problem, counts, dist, res.stats, band, as_float=as_float)
 
 
 def cci_template(n_celltypes, n_conditions, lri_order, ct_code, cond_code=None):
