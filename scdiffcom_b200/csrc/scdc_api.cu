@@ -305,6 +305,9 @@ struct scdc_handle {
     bool k2_done = false;
     int B = 0, k2_launches = 0;
     cudaEvent_t k2_t0 = nullptr, k2_t1 = nullptr;
+    // differential mode: pass 1 of batch 0 was launched ahead too (next to that scatter); p1_ev marks its end
+    bool p1_done = false;
+    cudaEvent_t p1_ev = nullptr;
   } pre;
 };
 
@@ -323,6 +326,7 @@ int prelaunch_labels(scdc_handle* h, const scdc_options* o);
 int upload_matrix_with_early_reduction(scdc_handle* h, const scdc_problem* p, const scdc_options* o,
                                        std::atomic<int>& genes_valid, std::atomic<bool>& matrix_done, const int& matrix_rc);
 int launch_early_scatter(scdc_handle* h, const scdc_options* o);
+int launch_early_pass1(scdc_handle* h, const scdc_options* o, cudaStream_t sp);
 
 int count_sm100_devices(std::vector<int>* ids) {
   int n = 0;
@@ -475,7 +479,7 @@ void scdc_release(scdc_handle* h) {
   cudaSetDevice(h->device);
   const int h_device = h->device;
   cudaStream_t s0 = h->stream, s1 = h->stream_labels, s2 = h->stream_score;
-  cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1, e2 = h->pre.k2_t0, e3 = h->pre.k2_t1;
+  cudaEvent_t e0 = h->pre.t0, e1 = h->pre.t1, e2 = h->pre.k2_t0, e3 = h->pre.k2_t1, e4 = h->pre.p1_ev;
   if (s1) cudaStreamSynchronize(s1);  // e.g. labels drawn ahead of a run that never happened
   if (s2) cudaStreamSynchronize(s2);
   {
@@ -502,6 +506,7 @@ void scdc_release(scdc_handle* h) {
   if (e1) cudaEventDestroy(e1);
   if (e2) cudaEventDestroy(e2);
   if (e3) cudaEventDestroy(e3);
+  if (e4) cudaEventDestroy(e4);
 }
 
 // Installs the tested rows (sub_cci_template_iter + observed vectors) on a handle: row tables, NA mask, K3 work list,
@@ -817,6 +822,7 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     // active genes. They are launched now; the pass-1 copy of the matrix and the rows are built and uploaded on the copy
     // stream (and allocated in its order) while that kernel runs. run_device then skips batch 0's k_scatter.
     cudaStream_t s_up = s;
+    struct TmpStream { cudaStream_t s = nullptr; ~TmpStream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } } rows_stream;
     cudaEvent_t ev_matrix;   // the matrix, the labels and the small tables are on the device
     CU(cudaEventCreateWithFlags(&ev_matrix, cudaEventDisableTiming));
     struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } ev_matrix_del{ev_matrix};
@@ -824,7 +830,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
     cudaEvent_t ev_sort;     // the pass-1 copy is built (when it was built on another stream)
     CU(cudaEventCreateWithFlags(&ev_sort, cudaEventDisableTiming));
     EvDel ev_sort_del{ev_sort};
-    bool sort_pending = false;
     if (o_hint && C == 2 && h->pre.valid && !o_hint->return_distributions && !env_int("SCDC_NO_EARLY_REDUCE", 0) &&
         p->n_rows > 0) {
       h->R = p->n_rows;
@@ -834,7 +839,12 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       if (rc) return rc;
       // the rows' uploads and small kernels go to the HIGH-priority label stream (idle by now): on a low-priority stream
       // their blocks starved behind the scatter's 24 k blocks and create waited ~350 ms for them (SCDC_TIMING, config 5)
-      if (h->pre.k2_done) s_up = h->stream_labels;
+      if (h->pre.k2_done) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&rows_stream.s, cudaStreamNonBlocking, hi));
+        s_up = rows_stream.s;   // (the label stream gets the sort and batch 0's pass 1 below)
+      }
       if (hook && h->pre.k2_done) {
         rc = hook->matrix_ready(h.get());
         if (rc) return rc;
@@ -853,9 +863,10 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       rc = build_pass1_copy(h.get(), s_sort);
       if (rc) return rc;
       if (s_sort != s) {
+        rc = launch_early_pass1(h.get(), o_hint, s_sort);   // batch 0's pass 1 next to batch 0's scatter
+        if (rc) return rc;
         CU(cudaEventRecord(ev_sort, s_sort));
-        CU(cudaStreamWaitEvent(s, ev_sort, 0));  // everything later on the compute stream sees the pass-1 copy
-        sort_pending = true;
+        CU(cudaStreamWaitEvent(s, ev_sort, 0));  // everything later on the compute stream sees the pass-1 copy (and M1 of batch 0)
       }
     }
     AllocScope up_scope(s_up);
@@ -872,7 +883,6 @@ static int create_impl(const scdc_problem* p, int32_t device, scdc_handle** out,
       // memory on that stream was enqueued before ev_matrix; the rows went through the copy stream.
       CU(cudaStreamSynchronize(s_up));
       CU(cudaEventSynchronize(ev_matrix));
-      if (sort_pending) CU(cudaEventSynchronize(ev_sort));
     } else {
       CU(cudaStreamSynchronize(s));  // host staging vectors die at scope exit
     }
@@ -1108,15 +1118,21 @@ int pick_batch(const scdc_handle* h, const scdc_options* o) {
     // equal batches: the reduction always runs whole batches, so n batches of the smallest multiple of q that covers
     // iterations / n waste at most q - 1 replicates per batch (10 000 -> 1 x 10 112 instead of 3 x 4096); among the batch
     // counts that fit the memory budget (and up to twice the minimum) take the one that pads least
-    // (Counting whole scatter blocks of W warps x 32 J replicates as well — config 5: 7 x 1792 replicates = 7 x 56 full
-    // chunks instead of 5 x 2560 = 5 x 80 chunks in 84 slots — was measured SLOWER, 1969 vs 1900 ms of reduction per 12 500
-    // replicates: every batch pays the tails of three kernels.)
+    // "Pads" counts what the scatter really runs: whole blocks of W warps x 32 J replicates (config 5, 12 500 replicates:
+    // 5 x 2560 runs 5 x 84 chunks for 80 useful ones each, 7 x 1792 runs 7 x 56 full ones). SCDC_BATCH_RULE=0: plain padding.
+    const bool block_aware = env_int("SCDC_BATCH_RULE", 1) != 0;
     const long long n_min = (o->iterations + B - 1) / B;
     long long best_B = 0, best_total = 0;
-    for (long long n = n_min; n <= 2 * n_min; ++n) {
+    for (long long n = n_min; n <= (block_aware ? 3 * n_min + 1 : 2 * n_min); ++n) {
       const long long Bn = (((o->iterations + n - 1) / n + q - 1) / q) * q;
       if (Bn > B) continue;
-      if (!best_B || n * Bn < best_total) { best_B = Bn; best_total = n * Bn; }
+      long long total = n * Bn;
+      if (block_aware) {
+        const ScatterPlan pn = plan_scatter(h, (int)Bn, o->precision == SCDC_FP32_FAST);
+        const long long slice = 32LL * pn.J * pn.W;
+        total = n * (((Bn + slice - 1) / slice) * slice);
+      }
+      if (!best_B || total < best_total) { best_B = Bn; best_total = total; }
     }
     if (best_B) B = best_B;
   } else {
@@ -1273,6 +1289,61 @@ int launch_early_scatter(scdc_handle* h, const scdc_options* o) {
   return SCDC_OK;
 }
 
+// Pass 1 of one batch (k_pass1_cond). persistent = a small grid whose warps pull (gene, chunk) items from a counter; used
+// when pass 1 runs next to the scatter.
+cudaError_t launch_pass1_kernel(scdc_handle* h, bool f32, int B, const uint8_t* bits1_b, void* M1b, cudaStream_t sp, int W,
+                                bool persistent) {
+  const int nWC = B / 256;
+  const long long tasks = (long long)h->n_active * nWC;
+  if (tasks <= 0) return cudaSuccess;
+  unsigned grid1 = (unsigned)((tasks + W - 1) / W);
+  int* counter = nullptr;
+  if (persistent) {
+    // blocks per SM: one next to the fp64 scatter (168 registers per thread at U = 32), two next to the fp32 one
+    // (measured, config 5 / config 3: fp64 1895 vs 2206 / 279 vs 286 ms of reduction per step, fp32 1219 vs 1158 / 162 vs 142)
+    grid1 = (unsigned)std::min<long long>(grid1, (long long)h->num_sms * std::max(1, env_int("SCDC_P1_BLOCKS", f32 ? 2 : 1)));
+    counter = h->p1_counter.p;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), sp);
+    if (e != cudaSuccess) return e;
+  }
+  const int U1 = env_int("SCDC_U1", 4);  // records per pipeline stage
+  auto go = [&](auto kern, auto* rec, auto* M1t) {
+    kern<<<grid1, W * 32, 0, sp>>>(h->G, h->n_active, h->T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p,
+                                   M1t, counter);
+  };
+  if (f32) {
+    if (U1 == 2) go(scdc::k_pass1_cond<float, 2>, h->rec_sf.p, static_cast<float*>(M1b));
+    else go(scdc::k_pass1_cond<float, 4>, h->rec_sf.p, static_cast<float*>(M1b));
+  } else {
+    if (U1 == 2) go(scdc::k_pass1_cond<double, 2>, h->rec_s.p, static_cast<double*>(M1b));
+    else go(scdc::k_pass1_cond<double, 4>, h->rec_s.p, static_cast<double*>(M1b));
+  }
+  return cudaGetLastError();
+}
+
+// One-shot call, differential mode: pass 1 of batch 0 right behind the device-side sort, on the same high-priority stream
+// `sp` (the pass-1 copy of the matrix is its input), so that it runs next to batch 0's scatter instead of after it.
+// run_device then skips it and waits for h->pre.p1_ev.
+int launch_early_pass1(scdc_handle* h, const scdc_options* o, cudaStream_t sp) {
+  if (!h->pre.k2_done || h->C != 2 || env_int("SCDC_NO_EARLY_PASS1", 0) || !env_int("SCDC_OVERLAP_PASS1", 1) ||
+      !env_int("SCDC_P1_PERSISTENT", 1))
+    return SCDC_OK;
+  const bool f32 = o->precision == SCDC_FP32_FAST;
+  const int B = h->pre.B;
+  AllocScope scope(sp);
+  CU(h->M1[0].ensure((size_t)(B / 32) * h->G * h->K * 32));
+  CU(h->p1_counter.ensure(1));
+  if (f32) {
+    int rc = ensure_f32_values(h, sp, true);
+    if (rc) return rc;
+  }
+  if (!h->pre.p1_ev) CU(cudaEventCreateWithFlags(&h->pre.p1_ev, cudaEventDisableTiming));
+  CU(launch_pass1_kernel(h, f32, B, reinterpret_cast<const uint8_t*>(h->bits1[0].p), h->M1[0].p, sp, env_int("SCDC_W1", 4), true));
+  CU(cudaEventRecord(h->pre.p1_ev, sp));
+  h->pre.p1_done = true;
+  return SCDC_OK;
+}
+
 // Runs replicates [o->perm_offset, o->perm_offset + o->iterations) on the handle's device; leaves uint32 counters in
 // h->counts (column-major [R][ncols]). Uploaded labels (if any) are indexed from 0 = first replicate of this call.
 int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_stats* st, cudaStream_t s) {
@@ -1294,8 +1365,10 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
   const bool pre_ok = !uploaded && h->pre.valid && h->pre.seed == o->seed && h->pre.perm_offset == o->perm_offset &&
                       h->pre.SB == SB && h->pre.J == pl.J;
   const bool early_k2 = pre_ok && h->pre.k2_done && h->pre.B == B && s == h->stream;
+  const bool early_p1 = early_k2 && h->pre.p1_done;
   h->pre.valid = false;  // consumed (or stale)
   h->pre.k2_done = false;
+  h->pre.p1_done = false;
   const int SBw = (int)(SB / 32);
   const bool pipelined = !uploaded && SB < iters_pad;
   const int nbuf = pipelined ? 2 : 1;
@@ -1497,39 +1570,18 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
     // then launched after the scatter on a second stream, in small blocks that fit into the registers / shared memory the
     // scatter leaves free on every SM, and joined before K3.
     const int ov1 = (C == 2) ? env_int("SCDC_OVERLAP_PASS1", 1) : 0;
-    // persistent = a small grid whose warps pull (gene, chunk) items from a counter; used when pass 1 runs next to the scatter
     auto launch_pass1 = [&](cudaStream_t sp, int W, bool persistent) -> cudaError_t {
-      const int nWC = B / 256;
-      const long long tasks = (long long)h->n_active * nWC;
-      unsigned grid1 = (unsigned)((tasks + W - 1) / W);
-      int* counter = nullptr;
-      if (persistent) {
-        // blocks per SM: one next to the fp64 scatter (168 registers per thread at U = 32), two next to the fp32 one
-        // (measured, config 5 / config 3: fp64 1895 vs 2206 / 279 vs 286 ms of reduction per step, fp32 1219 vs 1158 / 162 vs 142)
-        grid1 = (unsigned)std::min<long long>(grid1, (long long)h->num_sms * std::max(1, env_int("SCDC_P1_BLOCKS", f32 ? 2 : 1)));
-        counter = h->p1_counter.p;
-        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), sp);
-        if (e != cudaSuccess) return e;
-      }
-      const int U1 = env_int("SCDC_U1", 4);  // records per pipeline stage
-      auto go = [&](auto kern, auto* rec, auto* M1t) {
-        kern<<<grid1, W * 32, 0, sp>>>(G, h->n_active, T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p, M1t,
-                                       counter);
-      };
-      if (f32) {
-        if (U1 == 2) go(scdc::k_pass1_cond<float, 2>, h->rec_sf.p, static_cast<float*>(M1b));
-        else go(scdc::k_pass1_cond<float, 4>, h->rec_sf.p, static_cast<float*>(M1b));
-      } else {
-        if (U1 == 2) go(scdc::k_pass1_cond<double, 2>, h->rec_s.p, static_cast<double*>(M1b));
-        else go(scdc::k_pass1_cond<double, 4>, h->rec_s.p, static_cast<double*>(M1b));
-      }
-      return cudaGetLastError();
+      return launch_pass1_kernel(h, f32, B, bits1_b, M1b, sp, W, persistent);
     };
     if (C == 2 && !ov1) {
       CU(launch_pass1(s, 4, false));
       ++launches; ++reduce_launches;
     }
-    if (C == 2 && ov1) {
+    if (C == 2 && early_p1 && done == 0) {
+      // pass 1 of batch 0 was launched from scdc_create next to the early scatter (launch_early_pass1)
+      CU(cudaStreamWaitEvent(s, h->pre.p1_ev, 0));
+      ++launches; ++reduce_launches;
+    } else if (C == 2 && ov1) {
       // Pass 1 (FP64 / issue-slot bound, registers only) runs NEXT TO the pass-2 scatter (shared-memory-pipe bound): its
       // persistent grid of a block per SM is launched first, on a high-priority stream, so that its blocks are resident on
       // every SM before the scatter's blocks fill the rest; joined before K3.
@@ -1547,7 +1599,7 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
       CU(launch_scatter(h, pl, B, lab2_b, B, M2b, s));
       ++launches; ++reduce_launches;
     }
-    if (C == 2 && ov1) CU(cudaStreamWaitEvent(s, ov_join, 0));
+    if (C == 2 && ov1 && !(early_p1 && done == 0)) CU(cudaStreamWaitEvent(s, ov_join, 0));
     if (pipelined && (in_sb + B >= SB || done + B >= o->iterations)) { CU(cudaEventRecord(freed[buf], s)); freed_set[buf] = true; }
     // algorithmic bytes of this batch's reduction launches: matrix once per pass-kernel, labels, means out
     reduce_bytes += (double)C * ((double)h->nnz_active * (sv + 4.0) + 4.0 * (h->n_active + 1)) +
@@ -1875,7 +1927,7 @@ struct MultiGpuCall : CreateHook {
     m.dst[0] = src.p;
     for (int r = 1; r < W && m.bytes; ++r) {
       CU(cudaSetDevice(hs[r]->device));
-      AllocScope scope(hs[r]->stream);
+      AllocScope scope(bs[r]);   // allocated in the BROADCAST stream's order: the twin's compute stream may be busy
       auto& d = hs[r]->*member;
       CU(d.alloc(src.n));
       m.dst[r] = d.p;
@@ -1908,28 +1960,12 @@ struct MultiGpuCall : CreateHook {
     cudaGetLastError();  // "already enabled" / unsupported: peer copies then fall back to staging, still correct
   }
 
-  // Broadcast on the devices' broadcast streams, ordered after everything enqueued so far on every device's compute stream
-  // (the root's uploads, the twins' allocations); the twins' compute streams then wait for the arrival.
+  // Broadcast on the devices' broadcast streams. Nothing has to be waited for first: the root's buffers of a phase are
+  // complete on the host's clock when the phase runs (create_impl synchronises its uploads; what still runs on the root's
+  // compute stream is its first scatter, which must NOT be waited for), and the twins' buffers were allocated in the
+  // broadcast streams' own order. The twins' compute streams then wait for the arrival.
   int broadcast_ordered(const std::vector<Mirror>& ms) {
     const int W = (int)hs.size();
-    for (int r = 0; r < W; ++r) {
-      CU(cudaSetDevice(hs[r]->device));
-      cudaEvent_t ev;
-      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      cudaError_t e = cudaEventRecord(ev, hs[r]->stream);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(bs[r], ev, 0);
-      cudaEventDestroy(ev);
-      CU(e);
-    }
-    if (!use_nccl) {  // peer copies run on the twins' streams only: they must see the root's data
-      CU(cudaSetDevice(hs[0]->device));
-      cudaEvent_t ev;
-      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      cudaError_t e = cudaEventRecord(ev, hs[0]->stream);
-      for (int r = 1; r < W && e == cudaSuccess; ++r) e = cudaStreamWaitEvent(bs[r], ev, 0);
-      cudaEventDestroy(ev);
-      CU(e);
-    }
     int rc = broadcast_mirrors(hs, ms, use_nccl, bs);
     if (rc) return rc;
     for (int r = 1; r < W; ++r) {
@@ -1947,31 +1983,51 @@ struct MultiGpuCall : CreateHook {
   int phase_0(int root_device) {
     const int W = (int)hs.size();
     const scdc_problem* p = prob;
-    for (int r = 1; r < W; ++r) {
-      std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
-      if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
-      int rc = open_device_context(h.get(), devs[r]);
-      if (rc) return rc;
-      allow_peer(root_device, devs[r]);
-      allow_peer(devs[r], root_device);
-      if (getenv("SCDC_TIMING")) {
-        int can = -1;
-        cudaDeviceCanAccessPeer(&can, devs[r], root_device);
-        fprintf(stderr, "[scdc timing] device %d can access device %d directly: %d; broadcast / merge by %s\n", devs[r], root_device,
-                can, use_nccl ? "NCCL" : "peer copies");
+    std::vector<int> rcs((size_t)W, SCDC_OK);
+    std::vector<std::string> errs((size_t)W);
+    auto one = [&](int r) {   // one twin: context, labels from the host, its own label draw (a host thread per twin)
+      auto body = [&]() -> int {
+        std::unique_ptr<scdc_handle, void (*)(scdc_handle*)> h(new (std::nothrow) scdc_handle, scdc_release);
+        if (!h) return fail(SCDC_ENOMEM, "host allocation failed");
+        int rc = open_device_context(h.get(), devs[r]);
+        if (rc) return rc;
+        allow_peer(root_device, devs[r]);
+        allow_peer(devs[r], root_device);
+        if (getenv("SCDC_TIMING")) {
+          int can = -1;
+          cudaDeviceCanAccessPeer(&can, devs[r], root_device);
+          fprintf(stderr, "[scdc timing] device %d can access device %d directly: %d; broadcast / merge by %s\n", devs[r],
+                  root_device, can, use_nccl ? "NCCL" : "peer copies");
+        }
+        h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
+        h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
+        h->ncols = (h->C == 2) ? 3 + h->nS : 1;
+        h->nnz = (size_t)p->colptr[h->G];
+        h->one_shot = true;
+        hs[r] = h.release();
+        scdc_handle* hr = hs[r];
+        AllocScope scope(hr->stream);
+        rc = install_labels(hr, p, hr->stream);
+        if (!rc && os[r].iterations > 0) rc = prelaunch_labels(hr, &os[r]);
+        return rc;
+      };
+      try {
+        rcs[r] = body();
+      } catch (...) {
+        rcs[r] = fail(SCDC_ENOMEM, "exception while preparing device %d", devs[r]);
       }
-      h->N = p->n_cells; h->G = p->n_genes; h->T = p->n_celltypes; h->C = p->n_conditions; h->L = p->n_lri;
-      h->R = p->n_rows; h->nL = p->max_nL; h->nR = p->max_nR; h->K = h->C * h->T; h->nS = h->nL + h->nR;
-      h->ncols = (h->C == 2) ? 3 + h->nS : 1;
-      h->nnz = (size_t)p->colptr[h->G];
-      h->one_shot = true;
-      hs[r] = h.release();
-      scdc_handle* hr = hs[r];
-      AllocScope scope(hr->stream);
-      rc = install_labels(hr, p, hr->stream);
-      if (!rc && os[r].iterations > 0) rc = prelaunch_labels(hr, &os[r]);
-      if (rc) return rc;
+      if (rcs[r]) errs[r] = g_err;
+    };
+    std::vector<std::thread> th;
+    try {
+      for (int r = 2; r < W; ++r) th.emplace_back(one, r);
+    } catch (...) {
+      for (int r = (int)th.size() + 2; r < W; ++r) one(r);
     }
+    if (W > 1) one(1);
+    for (auto& t : th) t.join();
+    for (int r = 1; r < W; ++r)
+      if (rcs[r]) { g_err = errs[r]; return rcs[r]; }
     return SCDC_OK;
   }
 
@@ -2008,6 +2064,7 @@ struct MultiGpuCall : CreateHook {
         AllocScope sort_scope(s_sort);
         CU(cudaStreamWaitEvent(s_sort, ev, 0));
         rc = build_pass1_copy(h, s_sort);
+        if (!rc && early_launches) rc = launch_early_pass1(h, &os[r], s_sort);
         if (rc) return rc;
         CU(cudaEventRecord(ev, s_sort));
         CU(cudaStreamWaitEvent(h->stream, ev, 0));

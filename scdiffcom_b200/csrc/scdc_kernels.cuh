@@ -1195,7 +1195,25 @@ __global__ void k_scatter(int G, int K, int nCJ, const int* __restrict__ colptr,
           }
         }
       } else if (GRP == 2 && J == 1) {
-        // Two entries per step: both accumulators are loaded before either add.      } else {
+        // Two entries per step: both accumulators are loaded before either add. If the two labels coincide the second
+        // add continues from the first result, so the value stored last is ((acc + v1) + v2): the sequential sum, with a
+        // dependency chain of one shared-memory round trip per PAIR (matters when few warps are resident).
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+          VT* const p1 = reinterpret_cast<VT*>(accb + lb[u] * ROW);
+          VT* const p2 = reinterpret_cast<VT*>(accb + lb[u + 1] * ROW);
+          const VT a1 = *p1, a2 = *p2;
+          const VT r1 = a1 + val[u];
+          const VT r2 = ((lb[u] == lb[u + 1]) ? r1 : a2) + val[u + 1];
+          *p1 = r1;  // stores in entry order: for a repeated label the second store carries the sequential sum
+          *p2 = r2;
+          const pack_t e1 = src[u], e2 = src[u + 1];
+          val[u] = Ent<VT>::value(e1);
+          lb[u] = load_labels<J>(labbase + (uint64_t)e1.x * ustride);
+          val[u + 1] = Ent<VT>::value(e2);
+          lb[u + 1] = load_labels<J>(labbase + (uint64_t)e2.x * ustride);
+        }
+      } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (J == 1) {
