@@ -308,7 +308,9 @@ class Runner:
         peak, peak_src = load_peaks()
         ms_reduce = sum(s["ms_reduce"] for s in stats_acc)
         bytes_reduce = sum(s["reduce_bytes"] for s in stats_acc)
-        launches = sum(s["reduce_launches"] for s in stats_acc)
+        # one k_scatter launch per batch; in differential mode k_pass1_cond runs next to it (persistent grid on a second stream),
+        # so the unit is "one batch": the scatter's launch with pass 1 beside it, and the algorithmic bytes of both
+        launches = sum(s["reduce_launches"] for s in stats_acc) // prob.n_conditions
         achieved = bytes_reduce / (ms_reduce / 1e3) / 1e9 if ms_reduce > 0 else 0.0
         wavefronts = sum(s["reduce_wavefronts"] for s in stats_acc)
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
@@ -326,11 +328,13 @@ class Runner:
             with open(tpath) as fh:
                 traffic = json.load(fh).get(name if precision == "fp64" else f"{name}_{precision}")
         roofline = {
-            "bound": "hbm", "kernel": "k_scatter (+ k_pass1_cond in differential mode)", "achieved": achieved,
+            "bound": "hbm", "kernel": "k_scatter (k_pass1_cond runs beside it in differential mode; bytes and time of both)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "bytes_per_launch": bytes_reduce / max(1, launches), "ms_per_launch": ms_reduce / max(1, launches),
             "launches": launches, "binding_unit": pipe,
-            "note": "lane = replicate batching makes the kernel shared-memory-pipe bound, not HBM bound (DESIGN.md section 3)",
+            "note": "lane = replicate batching makes the kernel load-store-pipe bound, not HBM bound (DESIGN.md section 3); an ncu "
+                    "launch list serialises the two kernels, so k_pass1_cond shows its stand-alone time there (small persistent grid) "
+                    "while live it overlaps k_scatter: compare ms_per_launch with k_scatter's ncu time (profiles/NOTES_r2.md)",
             "unbatched_equivalent_gbs": (12.0 * prob.nnz * prob.n_conditions) * (iters * steps) / (ms_reduce / 1e3) / 1e9 if ms_reduce > 0 else None,
         }
         shares = {k: sum(s[k] for s in stats_acc) for k in ("ms_labels", "ms_reduce", "ms_score", "ms_device")}

@@ -176,6 +176,33 @@ class PinnedStager {
     return rc;
   }
 
+  // Device-to-host through the same pair of pinned buffers: chunk i is DMA'd into pinned memory while the caller's
+  // `consume(chunk, offset, bytes)` works on chunk i - 1 (e.g. widens counters straight into the caller's array), so no
+  // pageable temporary of the whole size is needed. Returns cudaErrorNotSupported when no pinned slot is available.
+  template <typename F>
+  cudaError_t fetch(const void* src_dev, size_t bytes, cudaStream_t s, F&& consume) {
+    Slot* slot = acquire();
+    if (!slot) return cudaErrorNotSupported;
+    cudaError_t rc = cudaSuccess;
+    const long n_chunks = (long)((bytes + kChunk - 1) / kChunk);
+    auto issue = [&](long i) -> cudaError_t {
+      const size_t off = (size_t)i * kChunk, n = std::min(kChunk, bytes - off);
+      cudaError_t e = cudaMemcpyAsync(slot->buf[i & 1], static_cast<const char*>(src_dev) + off, n, cudaMemcpyDeviceToHost, s);
+      return e == cudaSuccess ? cudaEventRecord(slot->done[i & 1], s) : e;
+    };
+    if (n_chunks > 0) rc = issue(0);
+    for (long i = 0; i < n_chunks && rc == cudaSuccess; ++i) {
+      if (i + 1 < n_chunks) rc = issue(i + 1);
+      if (rc == cudaSuccess) rc = cudaEventSynchronize(slot->done[i & 1]);
+      if (rc != cudaSuccess) break;
+      const size_t off = (size_t)i * kChunk, n = std::min(kChunk, bytes - off);
+      consume(slot->buf[i & 1], off, n);
+    }
+    if (rc != cudaSuccess) cudaStreamSynchronize(s);
+    release(slot);
+    return rc;
+  }
+
  private:
   struct Slot {
     char* buf[2] = {nullptr, nullptr};
@@ -1774,26 +1801,43 @@ int run_device(scdc_handle* h, const scdc_options* o, double* dist_host, scdc_st
 int counts_to_host(const scdc_handle* h, uint32_t* dev, uint64_t* out, cudaStream_t s) {
   const size_t n = (size_t)h->R * h->ncols;
   if (!n) return SCDC_OK;
-  std::unique_ptr<uint32_t[]> raw32(new (std::nothrow) uint32_t[n]);
-  if (!raw32) return fail(SCDC_ENOMEM, "host allocation failed");
+  PhaseTimer pt;
   scdc::k_mark_na<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, h->obs.p, dev);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(raw32.get(), dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
   g_d2h_bytes += (double)n * sizeof(uint32_t);
   const int n_thr = (n > (1u << 20)) ? 4 : 1;
-  auto body = [&](int w) {
-    const size_t lo = n * w / n_thr, hi = n * (w + 1) / n_thr;
-    for (size_t i = lo; i < hi; ++i) out[i] = (raw32[i] == 0xFFFFFFFFu) ? SCDC_COUNT_NA : (uint64_t)raw32[i];
+  // widen [lo, hi) of a block of uint32 counters that starts at element `first` of the table
+  auto widen = [&](const uint32_t* raw, size_t first, size_t count) {
+    auto body = [&](int w) {
+      const size_t lo = count * w / n_thr, hi = count * (w + 1) / n_thr;
+      for (size_t i = lo; i < hi; ++i) out[first + i] = (raw[i] == 0xFFFFFFFFu) ? SCDC_COUNT_NA : (uint64_t)raw[i];
+    };
+    std::vector<std::thread> th;
+    try {
+      for (int w = 1; w < n_thr; ++w) th.emplace_back(body, w);
+    } catch (...) {
+      for (int w = (int)th.size() + 1; w < n_thr; ++w) body(w);
+    }
+    body(0);
+    for (auto& t : th) t.join();
   };
-  std::vector<std::thread> th;
-  try {
-    for (int w = 1; w < n_thr; ++w) th.emplace_back(body, w);
-  } catch (...) {
-    for (int w = (int)th.size() + 1; w < n_thr; ++w) body(w);
+  // pinned staging chunks: the DMA of chunk i + 1 runs while chunk i is widened into the caller's array
+  cudaError_t e = (n * sizeof(uint32_t) >= (4u << 20) && !getenv("SCDC_NO_STAGER"))
+                      ? g_stager.fetch(dev, n * sizeof(uint32_t), s,
+                                       [&](const char* chunk, size_t off, size_t bytes) {
+                                         widen(reinterpret_cast<const uint32_t*>(chunk), off / sizeof(uint32_t), bytes / sizeof(uint32_t));
+                                       })
+                      : cudaErrorNotSupported;
+  if (e == cudaErrorNotSupported) {  // small tables, or no pinned memory: one pageable copy
+    std::unique_ptr<uint32_t[]> raw32(new (std::nothrow) uint32_t[n]);
+    if (!raw32) return fail(SCDC_ENOMEM, "host allocation failed");
+    CU(cudaMemcpyAsync(raw32.get(), dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    widen(raw32.get(), 0, n);
+  } else {
+    CU(e);
   }
-  body(0);
-  for (auto& t : th) t.join();
+  pt.lap("counts: NA marks + D2H + widen");
   return SCDC_OK;
 }
 
