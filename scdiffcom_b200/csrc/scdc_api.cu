@@ -2087,7 +2087,7 @@ struct MultiGpuCall : CreateHook {
     PhaseTimer pt;
     int rc = broadcast_ordered(ms);
     if (rc) return rc;
-    if (pt.on) {  // SCDC_TIMING=1: wait for the copies so that their duration shows (changes the overlap it reports on)
+    if (pt.on && env_int("SCDC_TIMING", 1) >= 2) {  // SCDC_TIMING=2: wait for the copies so that their duration shows (changes the overlap it reports on)
       for (int r = 1; r < W; ++r) { cudaSetDevice(hs[r]->device); cudaStreamSynchronize(hs[r]->stream); }
       pt.lap("twins: matrix over NVLink");
     }
@@ -2119,7 +2119,33 @@ struct MultiGpuCall : CreateHook {
     return SCDC_OK;
   }
 
+  // phase 0 on a side thread (the calling thread is busy with the first device's upload)
+  int root_device = 0, p0_rc = SCDC_OK;
+  std::string p0_err;
+  std::thread p0_thread;
+  void start_phase_0() {
+    auto run = [this]() {
+      PhaseTimer pt;
+      p0_rc = phase_0(root_device);
+      if (p0_rc) p0_err = g_err;
+      pt.lap("twins: contexts + labels (side thread)");
+    };
+    try {
+      p0_thread = std::thread(run);
+    } catch (...) {
+      run();
+    }
+  }
+  int join_phase_0() {
+    if (p0_thread.joinable()) p0_thread.join();
+    if (p0_rc) g_err = p0_err;
+    return p0_rc;
+  }
+  ~MultiGpuCall() { if (p0_thread.joinable()) p0_thread.join(); }
+
   int matrix_ready(scdc_handle* root) override {
+    int rc = join_phase_0();
+    if (rc) return rc;
     hs[0] = root;
     return phase_a(true);
   }
@@ -2278,17 +2304,20 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   const bool use_nccl = mg.use_nccl = nccl_comms_for(mg.devs);
   rc = mg.open_broadcast_streams();
   if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
-  rc = mg.phase_0(ids[0]);
-  if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
-  pt.lap("perm_counts: twins' contexts + labels");
+  // the twins' contexts, labels and label draws are prepared on a side thread while this one validates and uploads the
+  // matrix to the first device; the hook (matrix_ready) joins it before the broadcast
+  mg.root_device = ids[0];
+  mg.start_phase_0();
   {
     scdc_handle* h0 = nullptr;
     rc = create_impl(p, ids[0], &h0, &os[0], &mg);  // W <= iterations / 128: every shard has replicates
-    if (rc) {  // twins made by the hook (mg.hs[0] is a handle create_impl has released itself)
-      const std::string keep = g_err;
-      hs[0] = nullptr;
+    const std::string keep = g_err;
+    const int rc0 = mg.join_phase_0();  // no-op when the hook has joined it already
+    if (rc || rc0) {  // twins made by phase 0 (after a failed create mg.hs[0] is a handle create_impl has released itself)
+      if (rc) { hs[0] = nullptr; g_err = keep; } else { hs[0] = h0; rc = rc0; }
+      const std::string keep2 = g_err;
       cleanup();
-      g_err = keep;
+      g_err = keep2;
       return rc;
     }
     hs[0] = h0;
@@ -2305,9 +2334,12 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     auto body = [&](int r) {
       struct Done { std::atomic<int>& n; ~Done() { n.fetch_sub(1); } } done_guard{workers_left};
       try {
-        const double h2d_before = g_h2d_bytes;
+        const double h2d_before = g_h2d_bytes, w0 = now_ms();
         if (o->interrupt) hs[r]->abort = &abort_flag;
         rcs[r] = run_device(hs[r], &os[r], nullptr, &sts[r], hs[r]->stream);
+        if (pt.on)
+          fprintf(stderr, "[scdc timing] device %d: run %.1f ms on the host clock (device %.1f: labels %.1f, reduce %.1f, score %.1f)\n",
+                  hs[r]->device, now_ms() - w0, sts[r].ms_device, sts[r].ms_labels, sts[r].ms_reduce, sts[r].ms_score);
         if (rcs[r]) errs[r] = g_err;
         sts[r].h2d_bytes = g_h2d_bytes - h2d_before;
       } catch (const std::bad_alloc&) {
@@ -2376,6 +2408,7 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
     cudaSetDevice(hs[r]->device);
     if (cudaStreamSynchronize(hs[r]->stream) != cudaSuccess) bad = bad ? bad : 3;
   }
+  pt.lap("perm_counts: counters merged across devices");
   if (!bad) {
     cudaSetDevice(hs[0]->device);
     if (counts_to_host(hs[0], hs[0]->counts.p, res->counts, hs[0]->stream)) bad = 3;
@@ -2407,7 +2440,9 @@ int scdc_perm_counts(const scdc_problem* p, const scdc_options* o, scdc_result* 
   (void)h2d0;
   res->stats.d2h_bytes = g_d2h_bytes - d2h0;
   res->stats.p2p_bytes = g_p2p_bytes - p2p0;
+  pt.lap("perm_counts: counters to the host");
   cleanup();
+  pt.lap("perm_counts: release");
   res->stats.ms_merge = now_ms() - t1;
   res->stats.ms_total = now_ms() - t0;
   res->stats.n_gpus = W;
