@@ -14,7 +14,7 @@ so the job at N GPUs is N * iterations replicates (N = 8: exactly the 100 k-perm
   value : replicates/s with the problem already resident in HBM (scdc_create done), counters left on the device.
   e2e   : the same job through the one-shot C-ABI call `scdc_perm_counts` with HOST buffers: problem validation,
           H2D of the matrix, device work, D2H of the counters — what `.Call` from R pays. At N > 1 rank 0 makes ONE
-          in-library call with n_gpus = N (host thread per device, NVLink broadcast of the matrix, NCCL all-reduce of the
+          in-library call with n_gpus = N (host thread per device, the matrix copied to the other devices over NVLink, NCCL all-reduce of the
           counters) while the other ranks wait at a CPU-side barrier: exactly the R caller's multi-GPU path.
   roofline : the group-sum kernels (k_scatter, + k_pass1_cond in differential mode), algorithmic bytes /
           their CUDA-event time.

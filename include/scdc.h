@@ -142,7 +142,7 @@ typedef struct scdc_stats {
   int64_t kernel_launches; /* all kernels launched by the call */
   int64_t batch_size;   /* replicates per launch actually used */
   int32_t n_gpus;       /* devices actually used */
-  int32_t reserved;     /* multi-GPU calls: 1 = NCCL did the broadcast / merge, 0 = peer copies (NCCL unavailable) */
+  int32_t reserved;     /* multi-GPU calls: 1 = NCCL merged the counters, 0 = peer copies + adds (NCCL unavailable) */
   double h2d_bytes;     /* bytes copied host -> device by the call (problem, rows, uploaded labels) */
   double d2h_bytes;     /* bytes copied device -> host (counters, distributions) */
   double p2p_bytes;     /* bytes copied device -> device over NVLink (multi-GPU: the problem is uploaded once and broadcast) */

@@ -65,7 +65,7 @@ class Stats(C.Structure):
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
-        d["used_nccl"] = int(self.reserved)   # multi-GPU calls: 1 = NCCL broadcast / all-reduce, 0 = peer copies
+        d["used_nccl"] = int(self.reserved)   # multi-GPU calls: 1 = NCCL all-reduce of the counters, 0 = peer copies + adds
         return d
 
 

@@ -12,7 +12,8 @@
 //   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE, SCDC_SCORE_BULK   K3 variants
 //   SCDC_NO_EARLY_REDUCE, SCDC_CHUNK_NNZ, SCDC_NO_PRELAUNCH   one-shot call: no reduction behind the upload, chunk size,
 //                            no label pre-launch
-//   SCDC_NO_NCCL=1, SCDC_BCAST_NCCL=1   multi-GPU call: peer copies + adds instead of ncclAllReduce / ncclBroadcast for the problem
+//   SCDC_NO_NCCL=1, SCDC_BCAST_NCCL=1   multi-GPU call: peer copies + adds instead of ncclAllReduce; ncclBroadcast instead of the copy
+//                            engines for the problem
 //   SCDC_NO_POOL, SCDC_NO_STAGER   plain cudaMalloc / plain pageable copies
 #include "../../include/scdc.h"
 #include "scdc_kernels.cuh"
@@ -1926,11 +1927,13 @@ int broadcast_mirrors(const std::vector<scdc_handle*>& hs, const std::vector<Mir
 }
 
 // ---- the twins of the first device's handle on the other devices of a multi-GPU call -----------------------------------
-// Nothing big is read from the caller's host arrays twice: the problem travels device to device over NVLink —
-// ncclBroadcast (cudaMemcpyPeerAsync when NCCL is unavailable: SCDC_NO_NCCL=1) on a dedicated high-priority stream per
-// device, because the devices' compute streams are busy with their first batch by then and an NCCL kernel that waits for
-// its peers at the rendezvous spins on SMs. Three phases, so that the twins lag the first device as little as possible:
-//   phase 0 (before create): contexts, the cell labels (N bytes, from the host) and each twin's own label draw;
+// Nothing big is read from the caller's host arrays twice: the problem travels device to device over NVLink by the copy
+// engines (cudaMemcpyPeerAsync, every twin pulls from the first device; SCDC_BCAST_NCCL=1: ncclBroadcast) on a dedicated
+// high-priority stream per device, because the devices' compute streams are busy with their first batch by then. The copy
+// engines are the default because they take no SMs: the ncclBroadcast kernels held SMs of every device during the first
+// batch and cost the 2-GPU call 0-40 ms (r2u). Three phases, so that the twins lag the first device as little as possible:
+//   phase 0 (side thread, while the calling thread uploads the matrix): contexts, the cell labels (N bytes, from the host)
+//            and each twin's own label draw;
 //   phase A (from create_impl's hook, as soon as the matrix is on the first device and its first scatter is running, while
 //            its host thread still has the rows to do): CSC matrix, LRI table, active genes; every twin then starts the
 //            scatter of its first batch and builds its pass-1 copy of the matrix locally (k_sort_by_celltype);
@@ -1941,6 +1944,9 @@ struct MultiGpuCall : CreateHook {
   std::vector<scdc_options> os;
   const scdc_problem* prob = nullptr;
   bool use_nccl = false, phase_a_done = false;
+  // SCDC_BCAST_NCCL=1: ncclBroadcast; 0: the devices' copy engines (cudaMemcpyPeerAsync), which take no SMs away from the
+  // first batch's kernels that are running on every device by then
+  bool bcast_nccl = env_int("SCDC_BCAST_NCCL", 0) != 0;
   std::vector<cudaStream_t> bs;    // broadcast stream of every device (high priority; the compute streams are busy)
 
   int open_broadcast_streams() {
@@ -2010,7 +2016,7 @@ struct MultiGpuCall : CreateHook {
   // broadcast streams' own order. The twins' compute streams then wait for the arrival.
   int broadcast_ordered(const std::vector<Mirror>& ms) {
     const int W = (int)hs.size();
-    int rc = broadcast_mirrors(hs, ms, use_nccl, bs);
+    int rc = broadcast_mirrors(hs, ms, use_nccl && bcast_nccl, bs);
     if (rc) return rc;
     for (int r = 1; r < W; ++r) {
       CU(cudaSetDevice(hs[r]->device));
