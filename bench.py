@@ -321,7 +321,7 @@ class Runner:
                 "wavefronts_per_launch": wavefronts / max(1, launches), "sm_mhz": sm_clock,
                 "note": "design wavefronts of k_scatter (entry broadcast + label load + accumulator read-modify-write) over the "
                         "CUDA-event time of the whole reduction (k_pass1_cond runs next to it in differential mode); ncu "
-                        "l1tex__throughput of k_scatter alone is in profiles/NOTES_r2.md (76.6 % at K = 120, 96.9 % at K = 50)"}
+                        "l1tex__throughput of k_scatter alone is in profiles/NOTES_r2.md (79.5 % at K = 120, 99.2 % at K = 50)"}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):

@@ -10,6 +10,7 @@
 //   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1, SCDC_P1_PERSISTENT, SCDC_P1_BLOCKS   k_pass1_cond: records per pipeline stage, warps per
 //                            block, run next to k_scatter (default 1) as a persistent grid (default 1) of n blocks per SM
 //   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE, SCDC_SCORE_BULK   K3 variants
+//   SCDC_K1_THREADS          k_draw_labels_keys2: 512 / 1024 threads per replicate block (0 = by shared-memory footprint)
 //   SCDC_NO_EARLY_REDUCE, SCDC_CHUNK_NNZ, SCDC_NO_PRELAUNCH   one-shot call: no reduction behind the upload, chunk size,
 //                            no label pre-launch
 //   SCDC_NO_NCCL=1, SCDC_BCAST_NCCL=1   multi-GPU call: peer copies + adds instead of ncclAllReduce; ncclBroadcast instead of the copy
@@ -992,8 +993,13 @@ cudaError_t launch_draw(scdc_handle* h, cudaStream_t s, uint64_t seed, int64_t p
       auto kern = scdc::k_draw_labels_keys2;
       if (kp2.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp2.smem);
       if (e != cudaSuccess) return e;
-      kern<<<B, 512, kp2.smem, s>>>(N, T, h->ct.p, h->expect.p, seed, perm0, kp2.NB1, kp2.cap1, kp2.NB2, kp2.cap2, out, dbg_cond,
-                                    dbg_ct, h->keyfail.p);
+      // one block per SM when the histograms need more than half of its shared memory (T = 60, 250 k cells: 156 KB): then
+      // 1024 threads instead of 512, so that the SM still has 32 warps to hide Philox's dependent multiply chain with
+      int k1_threads = (kp2.smem > 112 * 1024 && kp2.NB2 >= 1024) ? 1024 : 512;
+      const int k1_env = env_int("SCDC_K1_THREADS", 0);
+      if (k1_env == 512 || (k1_env == 1024 && kp2.NB2 >= 1024)) k1_threads = k1_env;
+      kern<<<B, k1_threads, kp2.smem, s>>>(N, T, h->ct.p, h->expect.p, seed, perm0, kp2.NB1, kp2.cap1, kp2.NB2, kp2.cap2, out,
+                                           dbg_cond, dbg_ct, h->keyfail.p);
     } else {
       auto kern = scdc::k_draw_labels_keys;
       if (kp.smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem);

@@ -416,6 +416,8 @@ __global__ void __launch_bounds__(256) k_draw_labels_keys(int N, int T, const ui
 // threshold per stratum; pass 2: one stratum at a time, NB2 bins, T - 1 thresholds) and rank exactly only the members of
 // the bins that contain a threshold. cond' lives in a shared-memory bitmap between the passes.
 // Output: replicate-major combined labels out[q][cell] = cond' * T + ct' (or the two debug arrays).
+// block = 512 or 1024 threads (a power of two <= NB2: the bin scan gives every thread NB2 / blockDim bins); the result does
+// not depend on it.
 // ------------------------------------------------------------------------------------------------------------------
 struct KeygenPlan2 {
   int ok;
@@ -455,7 +457,7 @@ __device__ __forceinline__ bool keygen_less_s(uint32_t ax, uint32_t x, uint32_t 
   return x < y;
 }
 
-__global__ void __launch_bounds__(512) k_draw_labels_keys2(int N, int T, const uint8_t* __restrict__ ct,
+__global__ void __launch_bounds__(1024) k_draw_labels_keys2(int N, int T, const uint8_t* __restrict__ ct,
                                                            const uint32_t* __restrict__ ngroup_u /*[2][T]*/, uint64_t seed,
                                                            int64_t perm0, int NB1, int cap1, int NB2, int cap2,
                                                            uint8_t* __restrict__ out, uint8_t* __restrict__ dbg_cond,
