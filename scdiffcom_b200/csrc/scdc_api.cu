@@ -7,8 +7,9 @@
 //   SCDC_BMAX, SCDC_SUPER_BATCH   cap of the reduction batch / of the label super-batch (replicates)
 //   SCDC_J, SCDC_J32, SCDC_W, SCDC_U, SCDC_PAIR   k_scatter: replicates per lane (fp64 / fp32), warps per block, (value, label)
 //                            slots per lane, entries per dependent step (0 / 1 / 2 -> 1 / 2 / 4)
-//   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1, SCDC_P1_PERSISTENT, SCDC_P1_BLOCKS   k_pass1_cond: records per pipeline stage, warps per
-//                            block, run next to k_scatter (default 1) as a persistent grid (default 1) of n blocks per SM
+//   SCDC_U1, SCDC_W1, SCDC_OVERLAP_PASS1, SCDC_P1_PERSISTENT, SCDC_P1_BLOCKS, SCDC_P1_STAGED   k_pass1_cond: records per pipeline stage,
+//                            warps per block, run next to k_scatter (default 1) as a persistent grid (default 1) of n blocks per
+//                            SM, records through a shared-memory ring (0 / 1; default by shape)
 //   SCDC_SCORE_V1, SCDC_SCORE_P, SCDC_SCORE_SMEM_KB, SCDC_SCORE_THREADS, SCDC_NO_FACT, SCDC_OVERLAP_SCORE, SCDC_SCORE_BULK   K3 variants
 //   SCDC_K1_THREADS          k_draw_labels_keys2: 512 / 1024 threads per replicate block (0 = by shared-memory footprint)
 //   SCDC_NO_EARLY_REDUCE, SCDC_CHUNK_NNZ, SCDC_NO_PRELAUNCH   one-shot call: no reduction behind the upload, chunk size,
@@ -1341,16 +1342,34 @@ cudaError_t launch_pass1_kernel(scdc_handle* h, bool f32, int B, const uint8_t* 
     if (e != cudaSuccess) return e;
   }
   const int U1 = env_int("SCDC_U1", 4);  // records per pipeline stage
+  // Records staged through a shared-memory ring (fewer load-store write-back cycles, which is what pass 1 takes from the
+  // scatter next to it): 4 warps at most, and — persistent form — only where the ring (+ 1 KB the system reserves per block)
+  // fits into what the scatter's resident blocks leave of the SM's 228 KB: launched first, this kernel would otherwise cost
+  // the scatter a block per SM (fp64 K = 60: two 7-warp blocks leave 2 KB)
+  // Measured (r2z, reduction per step, uniform loads -> ring): config 3 (fp64, K = 50, scatter at 99 % of the load-store pipe
+  // with 16 resident warps) 280.2 -> 237.1 ms; config 5 (fp64, K = 120, 7 warps, latency-bound at 79 %) 1803.9 -> 1804.5;
+  // config 5 fp32 (14 warps) 1137.9 -> 1143.3. Default: fp64 with more than 8 resident scatter warps per SM.
+  const int staged_env = env_int("SCDC_P1_STAGED", -1);
+  bool staged = staged_env != 0 && W <= 4 && persistent;
+  if (staged) {
+    const ScatterPlan pl = plan_scatter(h, B, f32);
+    const size_t blocks1 = (size_t)std::max(1, env_int("SCDC_P1_BLOCKS", f32 ? 2 : 1));
+    const size_t left = 233472 - std::min<size_t>(233472, (size_t)pl.blocks_per_sm * (pl.smem + 1024));
+    staged = left >= blocks1 * ((f32 ? 2048 : 4096) + 1024);
+    if (staged_env < 0) staged = staged && !f32 && pl.blocks_per_sm * pl.W > 8;
+  }
   auto go = [&](auto kern, auto* rec, auto* M1t) {
     kern<<<grid1, W * 32, 0, sp>>>(h->G, h->n_active, h->T, nWC, h->segptr.p, rec, bits1_b, B / 8, h->ngroup.p, h->gene_order.p,
                                    M1t, counter);
   };
   if (f32) {
-    if (U1 == 2) go(scdc::k_pass1_cond<float, 2>, h->rec_sf.p, static_cast<float*>(M1b));
-    else go(scdc::k_pass1_cond<float, 4>, h->rec_sf.p, static_cast<float*>(M1b));
+    if (U1 == 2) go(scdc::k_pass1_cond<float, 2, false>, h->rec_sf.p, static_cast<float*>(M1b));
+    else if (staged) go(scdc::k_pass1_cond<float, 4, true>, h->rec_sf.p, static_cast<float*>(M1b));
+    else go(scdc::k_pass1_cond<float, 4, false>, h->rec_sf.p, static_cast<float*>(M1b));
   } else {
-    if (U1 == 2) go(scdc::k_pass1_cond<double, 2>, h->rec_s.p, static_cast<double*>(M1b));
-    else go(scdc::k_pass1_cond<double, 4>, h->rec_s.p, static_cast<double*>(M1b));
+    if (U1 == 2) go(scdc::k_pass1_cond<double, 2, false>, h->rec_s.p, static_cast<double*>(M1b));
+    else if (staged) go(scdc::k_pass1_cond<double, 4, true>, h->rec_s.p, static_cast<double*>(M1b));
+    else go(scdc::k_pass1_cond<double, 4, false>, h->rec_s.p, static_cast<double*>(M1b));
   }
   return cudaGetLastError();
 }

@@ -976,10 +976,9 @@ __global__ void k_rec_to_float(size_t n, const uint4* __restrict__ in, uint2* __
 // ------------------------------------------------------------------------------------------------------------------
 // K2a: differential pass 1. Cell types are fixed, only the condition bit varies per replicate, so the entries of a
 // gene column, pre-sorted by (cell type, cell) [stable: ascending cell order inside every (cell type, cond') group is
-// kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 128 replicates
-// (4 per lane): one uniform 16-byte load brings the condition bits of a cell for all 128.
+// kept], need two register accumulators per replicate and no shared-memory scatter. A warp covers 256 replicates
+// (8 per lane, k_pass1_cond below).
 // M1 layout: [chunk32][gene][k][32 lanes] with k = cond * T + ct, value = sum / n_k.
-// grid.x = nGa * (Bpad/128) / warps-per-block (rounded up), block = 32 * W.
 // ------------------------------------------------------------------------------------------------------------------
 // acc1 += v if the condition bit is set, else acc0 += v, for the 8 replicates of a lane, branch-free and bit-identical to
 // the branchy form: vm = bit ? v : +0.0 (two FSEL on a predicate that R2P extracts for all 8 bits at once), acc1 += vm,
@@ -1038,14 +1037,22 @@ __global__ void k_bits_transpose8(size_t n_groups, uint32_t* __restrict__ bits) 
 // counter until none is left. Launched before the pass-2 scatter, its few blocks sit on every SM for the whole batch and
 // the scatter's blocks fill the rest of the SM (its shared memory, most of its registers): the two kernels run side by side
 // by construction instead of at the block scheduler's discretion. block = 32 * W.
-template <typename VT, int U>
+// STAGED (block <= 4 warps): the records of the gene column go through a 64-record ring per warp in shared memory — each
+// lane loads ONE record of the next 32 (coalesced, a block ahead, held in a register until the ring half is free), and the
+// groups read them back as broadcasts: 2 + 0.25 write-back cycles per record instead of the uniform load's 4 (fp32: 1.125
+// instead of 2). The ring spans the column, not the segment: the segments of a gene are contiguous in `rec`. 4 KB (fp32:
+// 2 KB) of static shared memory per block, so the launcher uses it only where that fits next to the scatter's blocks.
+template <typename VT, int U, bool STAGED>
 __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int nWC, const int* __restrict__ segptr,
                                                     const typename Ent<VT>::pack* __restrict__ rec,
                                                     const uint8_t* __restrict__ bits, int Bb,
                                                     const double* __restrict__ ngroup, const int* __restrict__ gene_order,
                                                     VT* __restrict__ M1, int* __restrict__ work_counter) {
   typedef typename Ent<VT>::pack pack_t;
+  static_assert(5 * U <= 32, "a loop iteration reads at most 32 records ahead of its base");
+  __shared__ pack_t ring_s[STAGED ? 4 * 64 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  pack_t* const ring = ring_s + (STAGED ? warp * 64 : 0);
   const long long n_tasks = (long long)nGa * nWC;  // nGa active genes (gene_order), G = layout stride of M1
   const int K = 2 * T;
   const pack_t zero = Ent<VT>::make(0, (VT)0);
@@ -1061,6 +1068,23 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
   const uint8_t* bitbase = bits + wc * 32 + lane;  // + cell * Bb: the byte with this lane's 8 condition bits
   asm("" : "+l"(bitbase));
   const uint32_t ubb = (uint32_t)Bb;  // the address is one IMAD.WIDE (u32 cell x u32 stride + 64-bit lane base)
+  // STAGED: record e of the column [col_beg, col_end) sits in ring[(e - col_beg) & 63] while filled - 64 <= e < filled;
+  // `ahead` = this lane's record of the block [filled, filled + 32), already loaded
+  int col_beg = 0, col_end = 0, filled = 0;
+  pack_t ahead = zero;
+  if (STAGED) {
+    col_beg = sp[0]; col_end = sp[T]; filled = col_beg;
+    if (col_beg + lane < col_end) ahead = __ldg(rec + col_beg + lane);
+  }
+  auto top_up = [&](int base) {  // makes [base, base + 32) resident; overwrites only records below base
+    while (filled < base + 32 && filled < col_end) {
+      __syncwarp();  // every lane has read what it needed of the half that is overwritten
+      ring[(filled - col_beg + lane) & 63] = ahead;
+      filled += 32;
+      ahead = (filled + lane < col_end) ? __ldg(rec + filled + lane) : zero;
+      __syncwarp();
+    }
+  };
   for (int t = 0; t < T; ++t) {
     const int beg = sp[t], end = sp[t + 1];
     VT a0[8], a1[8];
@@ -1071,7 +1095,10 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
       uint32_t B0[U], B1[U], B2[U];
       auto load_recs = [&](pack_t (&R)[U], int e0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) R[u] = (e0 + u < end) ? __ldg(rec + e0 + u) : zero;
+        for (int u = 0; u < U; ++u) {
+          if (STAGED) R[u] = (e0 + u < end) ? ring[(e0 + u - col_beg) & 63] : zero;
+          else R[u] = (e0 + u < end) ? __ldg(rec + e0 + u) : zero;
+        }
       };
       auto load_bits = [&](uint32_t (&B)[U], const pack_t (&R)[U]) {
 #pragma unroll
@@ -1083,10 +1110,12 @@ __global__ void __launch_bounds__(128) k_pass1_cond(int G, int nGa, int T, int n
           sel_add8<VT>(a1, a0, B[u], Ent<VT>::value(R[u]));
         }
       };
+      if (STAGED) top_up(beg);
       load_recs(R0, beg);
       load_bits(B0, R0);
       load_recs(R1, beg + U);
       for (int base = beg; base < end; base += 3 * U) {
+        if (STAGED) top_up(base);
         load_bits(B1, R1); load_recs(R2, base + 2 * U); accumulate(R0, B0);
         load_bits(B2, R2); load_recs(R0, base + 3 * U); accumulate(R1, B1);   // past the end: zero records, bit-neutral
         load_bits(B0, R0); load_recs(R1, base + 4 * U); accumulate(R2, B2);
